@@ -1,0 +1,388 @@
+// hvs_engine.cu -- the C ABI of include/hvs.h: engine lifetime, solve orchestration, statistics.
+//
+// One engine = one GPU = one stream.  solve():
+//   H2D queries -> K1 slice search -> D2H slices -> host planner -> H2D work lists
+//   -> K4 direct scan (sparse slices)  +  K2/K3 tile sweeps (shared slices) -> K5 finalize -> D2H ids.
+// No CPU fallback anywhere: every distance and every selection runs in the CUDA kernels of this
+// library; the host only plans.
+#include <chrono>
+#include <cstring>
+#include <mutex>
+
+#include "hvs_engine.h"
+
+using namespace hvs;
+
+static thread_local std::string g_create_err = "";
+
+#define EFAIL(code, msg)            \
+    do {                            \
+        e->err = (msg);             \
+        return (code);              \
+    } while (0)
+
+#define ECUDA(call)                                                                        \
+    do {                                                                                   \
+        cudaError_t _c = (call);                                                           \
+        if (_c != cudaSuccess) {                                                           \
+            if (e->err.empty()) e->err = std::string(#call) + ": " + cudaGetErrorString(_c);                    \
+            return HVS_ERR_CUDA;                                                           \
+        }                                                                                  \
+    } while (0)
+
+extern "C" uint32_t hvs_abi_version(void) { return HVS_ABI_VERSION; }
+
+extern "C" const char *hvs_last_error(const hvs_engine *e)
+{
+    if (!e) return g_create_err.c_str();
+    return e->err.c_str();
+}
+
+extern "C" int hvs_create(hvs_engine **out, const hvs_config *cfg)
+{
+    if (!out) { g_create_err = "hvs_create: out is NULL"; return HVS_ERR_INVALID; }
+    *out = nullptr;
+    hvs_config c{};
+    c.device = -1;
+    if (cfg) {
+        if (cfg->struct_size < 16 || cfg->struct_size > sizeof(hvs_config)) {
+            g_create_err = "hvs_create: bad hvs_config.struct_size";
+            return HVS_ERR_INVALID;
+        }
+        std::memcpy(&c, cfg, cfg->struct_size);
+    }
+    if (c.mode > HVS_MODE_TENSOR) { g_create_err = "hvs_create: unknown mode"; return HVS_ERR_INVALID; }
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0) {
+        g_create_err = std::string("hvs_create: no CUDA device (") + cudaGetErrorString(ce) +
+                       "); this engine has no CPU fallback";
+        cudaGetLastError();
+        return HVS_ERR_NO_DEVICE;
+    }
+    int dev = c.device;
+    if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) dev = 0; }
+    if (dev >= ndev) { g_create_err = "hvs_create: device ordinal out of range"; return HVS_ERR_INVALID; }
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess || prop.major != 10) {
+        g_create_err = "hvs_create: device is not sm_100 (Blackwell B200); kernels are built for sm_100a only";
+        return HVS_ERR_NO_DEVICE;
+    }
+    if (cudaSetDevice(dev) != cudaSuccess) { g_create_err = "hvs_create: cudaSetDevice failed"; return HVS_ERR_CUDA; }
+    hvs_engine *e = new (std::nothrow) hvs_engine();
+    if (!e) { g_create_err = "hvs_create: out of host memory"; return HVS_ERR_NOMEM; }
+    e->device = dev;
+    e->mode = c.mode;
+    e->id_offset = c.id_offset;
+    e->sm_count = prop.multiProcessorCount;
+    if (c.stream) { e->stream = (cudaStream_t)c.stream; e->own_stream = false; }
+    else {
+        if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            g_create_err = "hvs_create: cudaStreamCreate failed";
+            delete e;
+            return HVS_ERR_CUDA;
+        }
+        e->own_stream = true;
+    }
+    for (auto &ev : e->ev) cudaEventCreate(&ev);
+    e->stats.struct_size = sizeof(hvs_stats);
+    *out = e;
+    return HVS_OK;
+}
+
+extern "C" void hvs_destroy(hvs_engine *e)
+{
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    Index &ix = e->index;
+    for (int a = 0; a < 2; ++a) { ix.x[a].release(); ix.ids[a].release(); ix.xnorm[a].release(); ix.xb[a].release(); }
+    ix.keys_t.release(); ix.keys_ct.release(); ix.tail.release(); ix.inv_t.release();
+    DevBuf *bufs[] = {&e->d_queries, &e->d_out, &e->d_slices, &e->d_direct_q, &e->d_items, &e->d_item_q, &e->d_tile_q,
+                      &e->d_qoff, &e->d_qlists, &e->d_cand, &e->d_cand_cnt, &e->d_scratch, &e->d_flags,
+                      &e->d_work_counter, &e->d_rescore_ids, &e->d_rescore_out};
+    for (DevBuf *b : bufs) b->release();
+    e->h_slices.release(); e->h_stage.release();
+    for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
+    if (e->own_stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+static float ev_ms(cudaEvent_t a, cudaEvent_t b)
+{
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) { cudaGetLastError(); return 0.f; }
+    return ms;
+}
+
+extern "C" int hvs_index_build_device(hvs_engine *e, const float *rows_dev, uint32_t n, float sample_proportion)
+{
+    if (!e) return HVS_ERR_INVALID;
+    e->err.clear();
+    if (!rows_dev) EFAIL(HVS_ERR_INVALID, "hvs_index_build: rows is NULL");
+    if (n < HVS_K)
+        EFAIL(HVS_ERR_INVALID, "hvs_index_build: n < 100 (the reference's pad rule reads nodes[n-s], include/baseline.hpp:138-147)");
+    if (!(sample_proportion >= 0.f)) EFAIL(HVS_ERR_INVALID, "hvs_index_build: sample_proportion must be >= 0");
+    ECUDA(cudaSetDevice(e->device));
+    cudaEventRecord(e->ev[0], e->stream);
+    cudaError_t c = index_build_device(e, rows_dev, n, sample_proportion);
+    if (c != cudaSuccess) { if (e->err.empty()) e->err = cudaGetErrorString(c); return HVS_ERR_CUDA; }
+    cudaEventRecord(e->ev[1], e->stream);
+    ECUDA(cudaStreamSynchronize(e->stream));
+    e->stats.ms_index_build = ev_ms(e->ev[0], e->ev[1]);
+    e->stats.n = e->index.n;
+    e->stats.n_total = e->index.n_total;
+    return HVS_OK;
+}
+
+extern "C" int hvs_index_build(hvs_engine *e, const float *rows_host, uint32_t n, float sample_proportion)
+{
+    if (!e) return HVS_ERR_INVALID;
+    e->err.clear();
+    if (!rows_host) EFAIL(HVS_ERR_INVALID, "hvs_index_build: rows is NULL");
+    if (n < HVS_K)
+        EFAIL(HVS_ERR_INVALID, "hvs_index_build: n < 100 (the reference's pad rule reads nodes[n-s], include/baseline.hpp:138-147)");
+    ECUDA(cudaSetDevice(e->device));
+    DevBuf rows;
+    size_t bytes = (size_t)n * DROW * 4;
+    if (rows.ensure(bytes) != cudaSuccess) { cudaGetLastError(); EFAIL(HVS_ERR_NOMEM, "hvs_index_build: device allocation for D failed"); }
+    cudaError_t c = cudaMemcpyAsync(rows.p, rows_host, bytes, cudaMemcpyHostToDevice, e->stream);
+    if (c == cudaSuccess) c = cudaStreamSynchronize(e->stream);
+    if (c != cudaSuccess) { rows.release(); e->err = std::string("hvs_index_build: H2D of D: ") + cudaGetErrorString(c); return HVS_ERR_CUDA; }
+    int rc = hvs_index_build_device(e, rows.as<float>(), n, sample_proportion);
+    rows.release();
+    return rc;
+}
+
+// ---- solve ----------------------------------------------------------------------------------
+static int solve_impl(hvs_engine *e, const float *q_dev, uint32_t m, bool partial, uint32_t *out_ids, float *out_dist,
+                      uint32_t *out_count)
+{
+    hvs_stats &st = e->stats;
+    st.m = m;
+    st.pairs = st.pairs_computed = st.rows_union = 0;
+    st.n_direct = st.n_tile = st.n_items_ffma = st.n_items_tensor = st.n_fallback = st.launches = 0;
+    st.ms_plan = st.ms_direct = st.ms_tile = st.ms_tile_ffma = st.ms_tile_tensor = st.ms_finalize = st.ms_solve_device = 0.f;
+    if (!m) return HVS_OK;
+    cudaStream_t s = e->stream;
+    ECUDA(e->d_slices.ensure((size_t)m * sizeof(QSlice)));
+    ECUDA(e->h_slices.ensure((size_t)m * sizeof(QSlice)));
+    QSlice *d_sl = e->d_slices.as<QSlice>();
+
+    cudaEventRecord(e->ev[2], s);
+    ECUDA(launch_plan_search(e, q_dev, m, d_sl));
+    st.launches++;
+    ECUDA(cudaMemcpyAsync(e->h_slices.p, d_sl, (size_t)m * sizeof(QSlice), cudaMemcpyDeviceToHost, s));
+    ECUDA(cudaStreamSynchronize(s));
+
+    PlanParams pp;
+    pp.mode = e->mode;
+    pp.tensor_available = tensor_path_available() && e->index.xb[0].p != nullptr;
+    Plan &P = e->plan;
+    plan_build(e->h_slices.as<QSlice>(), m, pp, P);
+    st.pairs = P.pairs;
+    st.pairs_computed = P.pairs_computed;
+    st.n_direct = (uint32_t)P.direct_q.size();
+    st.n_tile = (uint32_t)P.tile_q.size();
+    st.n_items_ffma = P.n_ffma;
+    st.n_items_tensor = P.n_tensor;
+
+    // upload work lists (one staging buffer, one copy per list)
+    const size_t b_direct = P.direct_q.size() * 4, b_items = P.items.size() * sizeof(TileItem), b_itemq = P.item_q.size() * 4,
+                 b_tileq = P.tile_q.size() * 4, b_qoff = P.q_list_off.size() * 4, b_ql = P.q_lists.size() * 4;
+    ECUDA(e->h_stage.ensure(b_direct + b_items + b_itemq + b_tileq + b_qoff + b_ql + 64));
+    unsigned char *hs = e->h_stage.as<unsigned char>();
+    size_t o = 0;
+    auto up = [&](DevBuf &db, const void *src, size_t bytes) -> cudaError_t {
+        if (!bytes) return cudaSuccess;
+        cudaError_t c = db.ensure(bytes);
+        if (c != cudaSuccess) return c;
+        std::memcpy(hs + o, src, bytes);
+        c = cudaMemcpyAsync(db.p, hs + o, bytes, cudaMemcpyHostToDevice, s);
+        o += (bytes + 15) & ~(size_t)15;
+        return c;
+    };
+    ECUDA(up(e->d_direct_q, P.direct_q.data(), b_direct));
+    ECUDA(up(e->d_items, P.items.data(), b_items));
+    ECUDA(up(e->d_item_q, P.item_q.data(), b_itemq));
+    ECUDA(up(e->d_tile_q, P.tile_q.data(), b_tileq));
+    ECUDA(up(e->d_qoff, P.q_list_off.data(), b_qoff));
+    ECUDA(up(e->d_qlists, P.q_lists.data(), b_ql));
+    cudaEventRecord(e->ev[3], s);
+
+    // K4: direct scans
+    if (!P.direct_q.empty()) {
+        ECUDA(launch_direct(e, q_dev, d_sl, e->d_direct_q.as<uint32_t>(), (uint32_t)P.direct_q.size(), partial, out_ids, out_dist, out_count));
+        st.launches++;
+    }
+    cudaEventRecord(e->ev[4], s);
+
+    // K2 / K3: tile sweeps, then K5
+    if (!P.items.empty()) {
+        ECUDA(e->d_cand.ensure((size_t)P.n_lists * KOUT * 8));
+        ECUDA(e->d_cand_cnt.ensure((size_t)P.n_lists * 4));
+        ECUDA(e->d_flags.ensure((size_t)m * 4));
+        ECUDA(cudaMemsetAsync(e->d_flags.p, 0, (size_t)m * 4, s));
+        const TileItem *d_items = e->d_items.as<TileItem>();
+        cudaEventRecord(e->ev[5], s);
+        if (P.n_ffma) {
+            ECUDA(launch_tile_ffma(e, q_dev, d_sl, d_items, 0, P.n_ffma, e->d_item_q.as<uint32_t>(), e->d_cand.as<uint64_t>(),
+                                   e->d_cand_cnt.as<uint32_t>(), e->d_flags.as<uint32_t>(), 1.0f));
+            st.launches++;
+        }
+        cudaEventRecord(e->ev[6], s);
+        if (P.n_tensor) {
+            ECUDA(launch_tile_tensor(e, q_dev, d_sl, d_items, P.n_ffma, P.n_tensor, e->d_item_q.as<uint32_t>(),
+                                     e->d_cand.as<uint64_t>(), e->d_cand_cnt.as<uint32_t>(), e->d_flags.as<uint32_t>()));
+            st.launches++;
+        }
+        cudaEventRecord(e->ev[7], s);
+        ECUDA(launch_finalize(e, q_dev, d_sl, e->d_tile_q.as<uint32_t>(), (uint32_t)P.tile_q.size(), e->d_qoff.as<uint32_t>(),
+                              e->d_qlists.as<uint32_t>(), e->d_cand.as<uint64_t>(), e->d_cand_cnt.as<uint32_t>(),
+                              e->d_flags.as<uint32_t>(), partial, out_ids, out_dist, out_count));
+        st.launches++;
+        cudaEventRecord(e->ev[8], s);
+        // queries whose candidate buffers overflowed their margin guarantee are re-solved exactly by K4
+        ECUDA(cudaMemcpyAsync(e->h_slices.p, e->d_flags.p, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
+        ECUDA(cudaStreamSynchronize(s));
+        const uint32_t *fl = e->h_slices.as<uint32_t>();
+        std::vector<uint32_t> redo;
+        for (uint32_t q : P.tile_q) if (fl[q]) redo.push_back(q);
+        if (!redo.empty()) {
+            ECUDA(e->d_scratch.ensure(redo.size() * 4));
+            ECUDA(cudaMemcpyAsync(e->d_scratch.p, redo.data(), redo.size() * 4, cudaMemcpyHostToDevice, s));
+            ECUDA(launch_direct(e, q_dev, d_sl, e->d_scratch.as<uint32_t>(), (uint32_t)redo.size(), partial, out_ids, out_dist, out_count));
+            ECUDA(cudaStreamSynchronize(s));   // redo lives on the host stack
+            st.launches++;
+            st.n_fallback = (uint32_t)redo.size();
+        }
+    }
+    cudaEventRecord(e->ev[9], s);
+    ECUDA(cudaStreamSynchronize(s));
+    ECUDA(cudaGetLastError());
+    st.ms_plan = ev_ms(e->ev[2], e->ev[3]);
+    st.ms_direct = ev_ms(e->ev[3], e->ev[4]);
+    if (!P.items.empty()) {
+        st.ms_tile_ffma = ev_ms(e->ev[5], e->ev[6]);
+        st.ms_tile_tensor = ev_ms(e->ev[6], e->ev[7]);
+        st.ms_tile = st.ms_tile_ffma + st.ms_tile_tensor;
+        st.ms_finalize = ev_ms(e->ev[7], e->ev[8]);
+    }
+    st.ms_solve_device = ev_ms(e->ev[2], e->ev[9]);
+    return HVS_OK;
+}
+
+static int check_solve_args(hvs_engine *e, const void *q, uint32_t m, const void *out)
+{
+    if (!e) return HVS_ERR_INVALID;
+    e->err.clear();
+    if (!e->index.built) EFAIL(HVS_ERR_STATE, "hvs_solve: hvs_index_build has not succeeded on this engine");
+    if (m && (!q || !out)) EFAIL(HVS_ERR_INVALID, "hvs_solve: NULL buffer");
+    if (cudaSetDevice(e->device) != cudaSuccess) EFAIL(HVS_ERR_CUDA, "cudaSetDevice failed");
+    return HVS_OK;
+}
+
+extern "C" int hvs_solve_device(hvs_engine *e, const float *queries_dev, uint32_t m, uint32_t *out_ids_dev)
+{
+    int rc = check_solve_args(e, queries_dev, m, out_ids_dev);
+    if (rc) return rc;
+    auto t0 = std::chrono::steady_clock::now();
+    e->stats.ms_h2d = e->stats.ms_d2h = 0.f;
+    rc = solve_impl(e, queries_dev, m, false, out_ids_dev, nullptr, nullptr);
+    e->stats.ms_solve_wall = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return rc;
+}
+
+extern "C" int hvs_solve(hvs_engine *e, const float *queries_host, uint32_t m, uint32_t *out_ids_host)
+{
+    int rc = check_solve_args(e, queries_host, m, out_ids_host);
+    if (rc) return rc;
+    if (!m) return HVS_OK;
+    auto t0 = std::chrono::steady_clock::now();
+    cudaStream_t s = e->stream;
+    ECUDA(e->d_queries.ensure((size_t)m * QROW * 4));
+    ECUDA(e->d_out.ensure((size_t)m * K * 4));
+    cudaEventRecord(e->ev[0], s);
+    ECUDA(cudaMemcpyAsync(e->d_queries.p, queries_host, (size_t)m * QROW * 4, cudaMemcpyHostToDevice, s));
+    cudaEventRecord(e->ev[1], s);
+    rc = solve_impl(e, e->d_queries.as<float>(), m, false, e->d_out.as<uint32_t>(), nullptr, nullptr);
+    if (rc) return rc;
+    cudaEventRecord(e->ev[10], s);
+    ECUDA(cudaMemcpyAsync(out_ids_host, e->d_out.p, (size_t)m * K * 4, cudaMemcpyDeviceToHost, s));
+    cudaEventRecord(e->ev[11], s);
+    ECUDA(cudaStreamSynchronize(s));
+    e->stats.ms_h2d = ev_ms(e->ev[0], e->ev[1]);
+    e->stats.ms_d2h = ev_ms(e->ev[10], e->ev[11]);
+    e->stats.ms_solve_wall = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return HVS_OK;
+}
+
+extern "C" int hvs_solve_partial_device(hvs_engine *e, const float *queries_dev, uint32_t m, float *out_dist_dev,
+                                        uint32_t *out_ids_dev, uint32_t *out_count_dev)
+{
+    int rc = check_solve_args(e, queries_dev, m, out_ids_dev);
+    if (rc) return rc;
+    if (m && (!out_dist_dev || !out_count_dev)) EFAIL(HVS_ERR_INVALID, "hvs_solve_partial_device: NULL buffer");
+    auto t0 = std::chrono::steady_clock::now();
+    rc = solve_impl(e, queries_dev, m, true, out_ids_dev, out_dist_dev, out_count_dev);
+    e->stats.ms_solve_wall = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return rc;
+}
+
+extern "C" int hvs_merge_partials_device(hvs_engine *e, const float *queries_dev, uint32_t m, uint32_t g,
+                                         const float *dist_dev, const uint32_t *ids_dev, const uint32_t *count_dev,
+                                         const float *tail_rows_dev, uint32_t n_total, uint32_t *out_ids_dev)
+{
+    if (!e) return HVS_ERR_INVALID;
+    e->err.clear();
+    if (!m) return HVS_OK;
+    if (!queries_dev || !dist_dev || !ids_dev || !count_dev || !tail_rows_dev || !out_ids_dev || !g)
+        EFAIL(HVS_ERR_INVALID, "hvs_merge_partials_device: NULL buffer or g == 0");
+    if (n_total < HVS_K) EFAIL(HVS_ERR_INVALID, "hvs_merge_partials_device: n_total < 100");
+    ECUDA(cudaSetDevice(e->device));
+    ECUDA(launch_merge_partials(e, queries_dev, m, g, dist_dev, ids_dev, count_dev, tail_rows_dev, n_total, out_ids_dev));
+    ECUDA(cudaStreamSynchronize(e->stream));
+    return HVS_OK;
+}
+
+extern "C" int hvs_rescore(hvs_engine *e, const float *queries_host, uint32_t m, const uint32_t *ids_host, float *out_dist_host)
+{
+    if (!e) return HVS_ERR_INVALID;
+    e->err.clear();
+    if (!e->index.built) EFAIL(HVS_ERR_STATE, "hvs_rescore: no index");
+    if (!m) return HVS_OK;
+    if (!queries_host || !ids_host || !out_dist_host) EFAIL(HVS_ERR_INVALID, "hvs_rescore: NULL buffer");
+    ECUDA(cudaSetDevice(e->device));
+    cudaStream_t s = e->stream;
+    ECUDA(e->d_queries.ensure((size_t)m * QROW * 4));
+    ECUDA(e->d_rescore_ids.ensure((size_t)m * K * 4));
+    ECUDA(e->d_rescore_out.ensure((size_t)m * K * 4));
+    ECUDA(cudaMemcpyAsync(e->d_queries.p, queries_host, (size_t)m * QROW * 4, cudaMemcpyHostToDevice, s));
+    ECUDA(cudaMemcpyAsync(e->d_rescore_ids.p, ids_host, (size_t)m * K * 4, cudaMemcpyHostToDevice, s));
+    ECUDA(launch_rescore(e, e->d_queries.as<float>(), m, e->d_rescore_ids.as<uint32_t>(), e->d_rescore_out.as<float>(), nullptr));
+    ECUDA(cudaMemcpyAsync(out_dist_host, e->d_rescore_out.p, (size_t)m * K * 4, cudaMemcpyDeviceToHost, s));
+    ECUDA(cudaStreamSynchronize(s));
+    return HVS_OK;
+}
+
+extern "C" int hvs_get_stats(const hvs_engine *e, hvs_stats *out)
+{
+    if (!e || !out) return HVS_ERR_INVALID;
+    uint32_t sz = out->struct_size;
+    if (sz < 8 || sz > sizeof(hvs_stats)) sz = sizeof(hvs_stats);
+    hvs_stats tmp = e->stats;
+    tmp.struct_size = sz;
+    std::memcpy(out, &tmp, sz);
+    return HVS_OK;
+}
+
+extern "C" int hvs_measure_ffma_peak(hvs_engine *e, uint32_t iters, float *out_tflops, float *out_sm_mhz)
+{
+    if (!e || !out_tflops) return HVS_ERR_INVALID;
+    e->err.clear();
+    ECUDA(cudaSetDevice(e->device));
+    float mhz = 0.f;
+    ECUDA(measure_ffma_peak(e, iters ? iters : 5, out_tflops, &mhz));
+    if (out_sm_mhz) *out_sm_mhz = mhz;
+    return HVS_OK;
+}

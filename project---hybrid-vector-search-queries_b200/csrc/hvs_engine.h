@@ -1,0 +1,159 @@
+// hvs_engine.h -- internal (non-ABI) declarations shared by the engine's translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/hvs.h"
+#include "hvs_common.cuh"
+
+namespace hvs {
+
+// grow-only device buffer
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct HostPinned {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+// The index: two re-ordered copies of D.
+struct Index {
+    uint32_t n_total = 0;      // rows given (n of baseline.hpp:71)
+    uint32_t n = 0;            // rows indexed (sn of baseline.hpp:74)
+    uint32_t id_offset = 0;
+    DevBuf x[2];               // [n][100] fp32
+    DevBuf ids[2];             // [n] u32
+    DevBuf xnorm[2];           // [n] f32
+    DevBuf xb[2];              // bf16 tile image for the tensor path: [n_pad][128] bf16 (cols 100..102 = split ||x||^2)
+    DevBuf keys_t;             // [n] u32  sorted ord(T)
+    DevBuf keys_ct;            // [n] u64  sorted ord(C)<<32 | ord(T)
+    DevBuf tail;               // [100][100] fp32: tail[s-1] = vector of row n_total - s  (pad rule)
+    DevBuf inv_t;              // [n_total] u32: original row -> arena-T row (0xFFFFFFFF if not indexed); rescore only
+    float xnorm_max = 0.f;     // max ||x||^2 over indexed rows (margin bound)
+    bool built = false;
+    Arena arena(int a) const
+    {
+        Arena r;
+        r.x = x[a].as<float>(); r.ids = ids[a].as<uint32_t>(); r.xnorm = xnorm[a].as<float>();
+        r.xb = xb[a].p;
+        return r;
+    }
+};
+
+// ---- tile work items (K2 / K3) ----------------------------------------------------------------
+constexpr int QT = 128;        // queries per tile item
+constexpr int KOUT = 128;      // candidates an item hands to finalize per query (<= this many)
+
+struct TileItem {              // one CTA-sized unit of work: <= 128 queries sweep arena rows [row_begin,row_end)
+    uint32_t arena;
+    uint32_t row_begin;
+    uint32_t row_end;
+    uint32_t nq;               // 1..128
+    uint32_t q_off;            // offset into the item-query list (item_q[q_off .. q_off+nq))
+    uint32_t out_off;          // first candidate-list index of this item (list = out_off + slot)
+    uint32_t kind;             // 0 = FFMA, 1 = tensor
+    uint32_t pad;
+};
+
+struct Plan {
+    std::vector<uint32_t> direct_q;       // queries for the direct scan kernel
+    std::vector<TileItem> items;          // sorted by decreasing cost
+    std::vector<uint32_t> item_q;         // query index per (item, slot)
+    std::vector<uint32_t> tile_q;         // queries that go through finalize
+    std::vector<uint32_t> q_list_off;     // CSR over tile_q: lists of each tile query  [tile_q.size()+1]
+    std::vector<uint32_t> q_lists;        // candidate-list indices
+    uint64_t pairs = 0, pairs_computed = 0;
+    uint32_t n_lists = 0;
+    uint32_t n_ffma = 0, n_tensor = 0;
+};
+
+struct PlanParams {
+    uint32_t mode = HVS_MODE_AUTO;
+    uint32_t chunk_rows = 1u << 17;       // max rows an item sweeps
+    uint32_t tensor_min_rows = 1u << 14;  // AUTO: items at least this long with >= tensor_min_q queries use K3
+    uint32_t tensor_min_q = 32;
+    double direct_cost_ratio = 12.0;      // tile pair vs direct pair throughput ratio
+    bool tensor_available = false;
+};
+
+void plan_build(const QSlice *slices, uint32_t m, const PlanParams &pp, Plan &out);
+
+}  // namespace hvs
+
+struct hvs_engine {
+    int device = 0;
+    uint32_t mode = HVS_MODE_AUTO;
+    uint32_t id_offset = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    std::string err;
+    hvs::Index index;
+    hvs_stats stats{};
+    // per-solve scratch (grow-only)
+    hvs::DevBuf d_queries, d_out, d_slices, d_direct_q, d_items, d_item_q, d_tile_q, d_qoff, d_qlists;
+    hvs::DevBuf d_cand, d_cand_cnt, d_scratch, d_flags, d_work_counter, d_rescore_ids, d_rescore_out;
+    hvs::HostPinned h_slices, h_stage;
+    cudaEvent_t ev[12]{};
+    hvs::Plan plan;
+};
+
+namespace hvs {
+// each returns cudaSuccess or the failing error (message left in e->err)
+cudaError_t index_build_device(hvs_engine *e, const float *rows_dev, uint32_t n_total, float sample_proportion);
+cudaError_t launch_plan_search(hvs_engine *e, const float *queries_dev, uint32_t m, QSlice *slices_dev);
+// K4: solve `nq` queries listed in q_list_dev (or all 0..nq-1 if null) by direct scan.
+// partial == false: writes out_ids[q][100] with the pad rule applied.
+// partial == true : writes out_dist/out_ids (ascending, unused = +inf/0xFFFFFFFF) and out_count, no pad.
+cudaError_t launch_direct(hvs_engine *e, const float *queries_dev, const QSlice *slices_dev,
+                          const uint32_t *q_list_dev, uint32_t nq, bool partial,
+                          uint32_t *out_ids, float *out_dist, uint32_t *out_count);
+cudaError_t launch_tile_ffma(hvs_engine *e, const float *queries_dev, const QSlice *slices_dev,
+                             const TileItem *items_dev, uint32_t item_begin, uint32_t n_items,
+                             const uint32_t *item_q_dev, uint64_t *cand_dev, uint32_t *cand_cnt_dev,
+                             uint32_t *flags_dev, float margin_scale);
+cudaError_t launch_tile_tensor(hvs_engine *e, const float *queries_dev, const QSlice *slices_dev,
+                               const TileItem *items_dev, uint32_t item_begin, uint32_t n_items,
+                               const uint32_t *item_q_dev, uint64_t *cand_dev, uint32_t *cand_cnt_dev,
+                               uint32_t *flags_dev);
+cudaError_t launch_finalize(hvs_engine *e, const float *queries_dev, const QSlice *slices_dev,
+                            const uint32_t *tile_q_dev, uint32_t n_tile_q, const uint32_t *qoff_dev,
+                            const uint32_t *qlists_dev, const uint64_t *cand_dev, const uint32_t *cand_cnt_dev,
+                            uint32_t *flags_dev, bool partial, uint32_t *out_ids, float *out_dist, uint32_t *out_count);
+cudaError_t launch_merge_partials(hvs_engine *e, const float *queries_dev, uint32_t m, uint32_t g,
+                                  const float *dist_dev, const uint32_t *ids_dev, const uint32_t *count_dev,
+                                  const float *tail_rows_dev, uint32_t n_total, uint32_t *out_ids_dev);
+cudaError_t launch_rescore(hvs_engine *e, const float *queries_dev, uint32_t m, const uint32_t *ids_dev, float *out_dev,
+                           const float *rows_unused);
+cudaError_t measure_ffma_peak(hvs_engine *e, uint32_t iters, float *tflops, float *mhz);
+bool tensor_path_available();
+}  // namespace hvs

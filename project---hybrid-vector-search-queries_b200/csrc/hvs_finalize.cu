@@ -1,0 +1,252 @@
+// hvs_finalize.cu -- K5: exact re-rank of the tile sweeps' candidate lists, the data-sharded merge,
+// the SaveKNNFull re-score, and the FFMA-peak microkernel used as the FP32 roofline denominator.
+//
+// K5 closes the exactness argument of hvs_margin.cuh: the candidate lists of K2/K3 hold every row
+// whose approximate score is within the margin of the running 100-th best, so the reference's
+// top-100 is among them; here each surviving row is re-scored with the reference's own arithmetic
+// (sequential fp32 sub/mul/add, include/baseline.hpp:53-64 -- bit-identical, hvs_common.cuh) and the
+// final 100 are chosen and ordered by (distance, id), then the pad rule (include/baseline.hpp:138-147)
+// is applied exactly as in the direct kernel.
+#include "hvs_engine.h"
+#include "hvs_margin.cuh"
+#include "hvs_topk.cuh"
+
+namespace hvs {
+
+namespace {
+constexpr int FT = 128;        // threads
+constexpr int P1CAP = 2048;    // approximate-score selection buffer
+constexpr int P1KEEP = 512;    // most rows that may sit inside the margin before we give up
+struct FinSmem {
+    TopBuf<P1CAP, true> p1;
+    TopBuf<P1KEEP + 128, false> p2;
+    alignas(16) float q[DIM];
+};
+}  // namespace
+
+__global__ void __launch_bounds__(FT)
+k_finalize(const float *__restrict__ queries, const QSlice *__restrict__ slices, const uint32_t *__restrict__ tile_q,
+           const uint32_t *__restrict__ qoff, const uint32_t *__restrict__ qlists, const uint64_t *__restrict__ cand,
+           const uint32_t *__restrict__ cand_cnt, uint32_t *__restrict__ flags, Arena a0, Arena a1,
+           const float *__restrict__ tail, uint32_t n_total, float xnorm_max, int tensor_lists, int partial,
+           uint32_t *__restrict__ out_ids, float *__restrict__ out_dist, uint32_t *__restrict__ out_count)
+{
+    __shared__ FinSmem S;
+    const int tid = threadIdx.x;
+    const uint32_t q = tile_q[blockIdx.x];
+    const QSlice sl = slices[q];
+    const Arena A = sl.arena == ARENA_T ? a0 : a1;
+    const uint32_t len = sl.end - sl.begin;
+    S.p1.init(tid);
+    S.p2.init(tid);
+    if (tid < DIM / 4)
+        reinterpret_cast<float4 *>(S.q)[tid] = reinterpret_cast<const float4 *>(queries + (size_t)q * QROW + 4)[tid];
+    __syncthreads();
+    // lists written by K3 carry bf16-level error, lists written by K2 fp32-level error
+    const float margin = tensor_lists ? margin_tensor(sl.qnorm, xnorm_max) : margin_ffma(sl.qnorm, xnorm_max);
+
+    // phase 1: the rows whose approximate score is within the margin of the global 100-th best
+    const uint32_t l0 = qoff[blockIdx.x], l1 = qoff[blockIdx.x + 1];
+    for (uint32_t li = l0; li < l1; ++li) {
+        const uint32_t list = qlists[li];
+        const uint32_t c = min(cand_cnt[list], (uint32_t)KOUT);
+        if ((uint32_t)tid < c) {
+            const uint64_t k = cand[(size_t)list * KOUT + tid];
+            const float s = okey_inv((uint32_t)(k >> 32));
+            if (s < S.p1.thr) {
+                const uint32_t slot = atomicAdd(&S.p1.cnt, 1u);
+                S.p1.cand[slot] = k;                         // cnt <= P1CAP - FT before every list
+            }
+        }
+        __syncthreads();
+        if (S.p1.cnt > (uint32_t)(P1CAP - FT)) S.p1.compact(tid, FT, margin, P1KEEP);
+    }
+    S.p1.compact(tid, FT, margin, P1KEEP);
+    if (S.p1.overflow && tid == 0) flags[q] = 1u;            // K4 re-solves this query
+
+    // phase 2: the reference's arithmetic on the survivors
+    const int c1 = (int)S.p1.cnt;
+    for (int i = tid; i < c1; i += FT) {
+        const uint32_t row = (uint32_t)S.p1.cand[i];
+        const float d = ref_dist_row(A.x + (size_t)row * DIM, S.q);
+        S.p2.cand[i] = pack_key(d, row);
+    }
+    if (tid == 0) S.p2.cnt = c1;
+    __syncthreads();
+    finish_query(S.p2, S.q, A, len, tail, n_total, q, partial != 0, out_ids, out_dist, out_count, tid, FT);
+}
+
+cudaError_t launch_finalize(hvs_engine *e, const float *queries_dev, const QSlice *slices_dev, const uint32_t *tile_q_dev,
+                            uint32_t n_tile_q, const uint32_t *qoff_dev, const uint32_t *qlists_dev, const uint64_t *cand_dev,
+                            const uint32_t *cand_cnt_dev, uint32_t *flags_dev, bool partial, uint32_t *out_ids,
+                            float *out_dist, uint32_t *out_count)
+{
+    if (!n_tile_q) return cudaSuccess;
+    const Index &ix = e->index;
+    k_finalize<<<n_tile_q, FT, 0, e->stream>>>(queries_dev, slices_dev, tile_q_dev, qoff_dev, qlists_dev, cand_dev, cand_cnt_dev,
+                                                flags_dev, ix.arena(0), ix.arena(1), ix.tail.as<float>(), ix.n_total,
+                                                ix.xnorm_max, e->plan.n_tensor ? 1 : 0, partial ? 1 : 0, out_ids,
+                                                out_dist, out_count);
+    return cudaGetLastError();
+}
+
+// ---- data-sharded merge (include/optimized_impl.h:337-385 Knn::merge, at GPU scale) -----------
+namespace {
+struct MergeSmem {
+    TopBuf<1024, false> top;
+    alignas(16) float q[DIM];
+    uint32_t total;
+};
+}  // namespace
+
+__global__ void __launch_bounds__(FT)
+k_merge_partials(const float *__restrict__ queries, uint32_t m, uint32_t g, const float *__restrict__ dist,
+                 const uint32_t *__restrict__ ids, const uint32_t *__restrict__ count, const float *__restrict__ tail_rows,
+                 uint32_t n_total, uint32_t *__restrict__ out_ids)
+{
+    __shared__ MergeSmem S;
+    const int tid = threadIdx.x;
+    const uint32_t q = blockIdx.x;
+    S.top.init(tid);
+    if (tid == 0) S.total = 0;
+    if (tid < DIM / 4)
+        reinterpret_cast<float4 *>(S.q)[tid] = reinterpret_cast<const float4 *>(queries + (size_t)q * QROW + 4)[tid];
+    __syncthreads();
+    for (uint32_t s = 0; s < g; ++s) {
+        const size_t base = ((size_t)s * m + q) * K;
+        if (tid < K) {
+            const uint32_t id = ids[base + tid];
+            const float d = dist[base + tid];
+            if (id != 0xffffffffu && d < S.top.thr) S.top.push(d, id);
+        }
+        if (tid == 0) {
+            const uint64_t t = (uint64_t)S.total + count[(size_t)s * m + q];
+            S.total = t > 0xffffffffull ? 0xffffffffu : (uint32_t)t;
+        }
+        __syncthreads();
+        if (S.top.cnt > 1024u - K) S.top.compact(tid, FT, 0.f, K);
+    }
+    __syncthreads();
+    // candidates are (distance, global id) already: finish by hand (no arena lookup)
+    if ((int)S.top.cnt > K) S.top.compact(tid, FT, 0.f, K);
+    int c = min((int)S.top.cnt, K);
+    const uint32_t total = S.total;
+    if (total < (uint32_t)K) {                  // pad rule, applied once, globally (baseline.hpp:138-147)
+        const int npad = K - (int)total;
+        for (int s = tid; s < npad; s += FT) {
+            const float *row = tail_rows + (size_t)(K - 1 - s) * DROW + 2;   // tail_rows[r] = global row n_total-100+r
+            float sum = 0.f;
+            for (int i = 0; i < DIM; ++i) { const float df = __fsub_rn(row[i], S.q[i]); sum = __fadd_rn(sum, __fmul_rn(df, df)); }
+            S.top.cand[c + s] = pack_key(sum, n_total - 1u - (uint32_t)s);
+        }
+        c += npad;
+    }
+    for (int i = c + tid; i < 256; i += FT) S.top.cand[i] = KEY_INF;
+    __syncthreads();
+    block_bitonic_sort(S.top.cand, 256, tid, FT);
+    for (int i = tid; i < K; i += FT) out_ids[(size_t)q * K + i] = (uint32_t)S.top.cand[i];
+}
+
+cudaError_t launch_merge_partials(hvs_engine *e, const float *queries_dev, uint32_t m, uint32_t g, const float *dist_dev,
+                                  const uint32_t *ids_dev, const uint32_t *count_dev, const float *tail_rows_dev,
+                                  uint32_t n_total, uint32_t *out_ids_dev)
+{
+    k_merge_partials<<<m, FT, 0, e->stream>>>(queries_dev, m, g, dist_dev, ids_dev, count_dev, tail_rows_dev, n_total, out_ids_dev);
+    return cudaGetLastError();
+}
+
+// ---- SaveKNNFull on the device (include/io.h:50-78) ---------------------------------------------
+__global__ void k_rescore(const float *__restrict__ queries, uint32_t m, const uint32_t *__restrict__ ids,
+                          const uint32_t *__restrict__ inv_t, const float *__restrict__ x_t, const float *__restrict__ tail,
+                          uint32_t n_total, uint32_t id_offset, float *__restrict__ out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)m * K) return;
+    const uint32_t q = (uint32_t)(i / K);
+    const uint32_t id = ids[i] - id_offset;
+    float d = __int_as_float(0x7fc00000);
+    if (id < n_total) {
+        const uint32_t pos = inv_t[id];
+        const float *x = nullptr;
+        if (pos != 0xffffffffu) x = x_t + (size_t)pos * DIM;
+        else if (n_total - 1u - id < (uint32_t)K) x = tail + (size_t)(n_total - 1u - id) * DIM;   // a pad row that was not indexed
+        if (x) d = ref_dist_row(x, queries + (size_t)q * QROW + 4);
+    }
+    out[i] = d;
+}
+
+cudaError_t launch_rescore(hvs_engine *e, const float *queries_dev, uint32_t m, const uint32_t *ids_dev, float *out_dev,
+                           const float *)
+{
+    const Index &ix = e->index;
+    const size_t total = (size_t)m * K;
+    k_rescore<<<(unsigned)((total + 127) / 128), 128, 0, e->stream>>>(queries_dev, m, ids_dev, ix.inv_t.as<uint32_t>(),
+                                                                        ix.x[ARENA_T].as<float>(), ix.tail.as<float>(),
+                                                                        ix.n_total, ix.id_offset, out_dev);
+    return cudaGetLastError();
+}
+
+// ---- FFMA peak ------------------------------------------------------------------------------------
+// The same 8x8 register outer product as K2's inner loop, with no memory traffic: what the FP32
+// pipes deliver on nvcc-scheduled FFMA.  This is the denominator of K2's roofline fraction
+// (MEASURED_PEAKS.json has no FP32 figure).
+__global__ void __launch_bounds__(256, 2) k_ffma_peak(float *__restrict__ out, int iters, long long *__restrict__ clk)
+{
+    float a[8], b[8], c[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a[i] = 1.0f + 1e-3f * (threadIdx.x + i); b[i] = 1.0f - 1e-3f * (threadIdx.x + 2 * i); }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) c[i][j] = 0.f;
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) c[i][j] = fmaf(a[i], b[j], c[i][j]);
+    }
+    const long long t1 = clock64();
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += c[i][j];
+    if (s == 12345.678f) out[0] = s;       // keeps the loop alive, never true in practice
+    if (threadIdx.x == 0 && blockIdx.x == 0) clk[0] = t1 - t0;
+}
+
+cudaError_t measure_ffma_peak(hvs_engine *e, uint32_t reps, float *tflops, float *mhz)
+{
+    DevBuf out;
+    cudaError_t c = out.ensure(64);
+    if (c != cudaSuccess) return c;
+    cudaMemsetAsync(out.p, 0, 64, e->stream);
+    const int iters = 20000, blocks = e->sm_count * 2;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    float best = 1e30f;
+    for (uint32_t r = 0; r < reps + 1; ++r) {        // first launch is the warm-up
+        cudaEventRecord(a, e->stream);
+        k_ffma_peak<<<blocks, 256, 0, e->stream>>>(out.as<float>(), iters, reinterpret_cast<long long *>(out.as<char>() + 16));
+        cudaEventRecord(b, e->stream);
+        c = cudaStreamSynchronize(e->stream);
+        if (c != cudaSuccess) break;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        if (r > 0 && ms < best) best = ms;
+    }
+    long long cyc = 0;
+    if (c == cudaSuccess) c = cudaMemcpy(&cyc, out.as<char>() + 16, 8, cudaMemcpyDeviceToHost);
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    out.release();
+    if (c != cudaSuccess) return c;
+    const double flop = 2.0 * 256.0 * (double)iters * 256.0 * (double)blocks;
+    *tflops = (float)(flop / ((double)best * 1e-3) / 1e12);
+    if (mhz) *mhz = (float)((double)cyc / ((double)best * 1e-3) / 1e6);
+    return cudaSuccess;
+}
+
+}  // namespace hvs

@@ -1,0 +1,176 @@
+// hvs_index.cu -- K0: the indexing phase.
+//
+// Replaces the per-query O(N) predicate scans of the reference (include/baseline.hpp:107-136,
+// include/optimized.hpp:84-117, include/optimized_parallel.hpp:105-138) with two radix-sorted,
+// re-laid-out copies of D so that every predicate is one contiguous row range:
+//   arena T  : rows ordered by ord(T)               -> types 0 (all rows) and 2 (l <= T <= r)
+//   arena CT : rows ordered by ord(C)<<32 | ord(T)  -> types 1 (C == v) and 3 (C == v, l <= T <= r)
+// Each arena holds the 100-d vectors as contiguous 400-byte rows (16-byte aligned, so a tile of
+// consecutive rows is ONE contiguous block that the TMA engine moves with a single 1-D bulk copy),
+// the original row ids, ||x||^2, and the sorted keys for binary search.  Never sees queries
+// (contest rule, README.md:68).  HBM-bound: ~2 sorts + 2 gathers of 400 B/row.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "hvs_engine.h"
+
+namespace hvs {
+
+__global__ void k_make_keys(const float *__restrict__ rows, uint32_t n, uint32_t *__restrict__ key_t,
+                            uint64_t *__restrict__ key_ct, uint32_t *__restrict__ perm)
+{
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    float2 ct = *reinterpret_cast<const float2 *>(rows + (size_t)j * DROW);   // rows are 408 B: 8-byte aligned
+    uint32_t kc = ord_key(ct.x), kt = ord_key(ct.y);
+    key_t[j] = kt;
+    key_ct[j] = ((uint64_t)kc << 32) | kt;
+    perm[j] = j;
+}
+
+// One warp per destination row: gather the vector of source row perm[p] into arena row p,
+// record its id and squared norm.  Source rows are only 8-byte aligned (408-byte pitch, vector at +8).
+__global__ void k_gather(const float *__restrict__ rows, const uint32_t *__restrict__ perm, uint32_t n,
+                         uint32_t id_offset, float *__restrict__ x, uint32_t *__restrict__ ids,
+                         float *__restrict__ xnorm, uint32_t *__restrict__ inv /* may be null */)
+{
+    uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n) return;
+    uint32_t src = perm[warp];
+    const float2 *s = reinterpret_cast<const float2 *>(rows + (size_t)src * DROW + 2);
+    float2 *d = reinterpret_cast<float2 *>(x + (size_t)warp * DIM);
+    float acc = 0.f;
+    float2 v = s[lane];
+    d[lane] = v;
+    acc = fmaf(v.x, v.x, acc); acc = fmaf(v.y, v.y, acc);
+    if (lane < DIM / 2 - 32) {
+        v = s[32 + lane];
+        d[32 + lane] = v;
+        acc = fmaf(v.x, v.x, acc); acc = fmaf(v.y, v.y, acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+        ids[warp] = src + id_offset;
+        xnorm[warp] = acc;
+        if (inv) inv[src] = warp;
+    }
+}
+
+// tail[s-1] = vector of row n_total - s, s = 1..100  (pad rule, include/baseline.hpp:138-147)
+__global__ void k_tail(const float *__restrict__ rows, uint32_t n_total, float *__restrict__ tail)
+{
+    uint32_t s = blockIdx.x + 1;
+    const float *src = rows + (size_t)(n_total - s) * DROW + 2;
+    for (int i = threadIdx.x; i < DIM; i += blockDim.x) tail[(s - 1) * DIM + i] = src[i];
+}
+
+__global__ void k_max_f32(const float *__restrict__ v, uint32_t n, uint32_t *__restrict__ out_bits)
+{
+    float m = 0.f;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float a = v[i];
+        if (a == a && a > m) m = a;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(m));   // non-negative floats order like their bits
+}
+
+void build_bf16_image(hvs_engine *e, int a);   // hvs_tile_tensor.cu
+
+#define CK(call)                                                                     \
+    do {                                                                             \
+        cudaError_t _e = (call);                                                     \
+        if (_e != cudaSuccess) {                                                     \
+            e->err = std::string(#call) + ": " + cudaGetErrorString(_e);             \
+            return _e;                                                               \
+        }                                                                            \
+    } while (0)
+
+cudaError_t index_build_device(hvs_engine *e, const float *rows, uint32_t n_total, float sample_proportion)
+{
+    Index &ix = e->index;
+    ix.built = false;
+    uint32_t n = (uint32_t)(sample_proportion * (float)n_total);   // include/baseline.hpp:74
+    if (n > n_total) n = n_total;
+    ix.n_total = n_total;
+    ix.n = n;
+    ix.id_offset = e->id_offset;
+    cudaStream_t st = e->stream;
+    const size_t n1 = n ? n : 1;
+
+    DevBuf key_t_in, key_ct_in, perm_in, perm_out, tmp, maxbits;
+    CK(key_t_in.ensure(n1 * 4));
+    CK(key_ct_in.ensure(n1 * 8));
+    CK(perm_in.ensure(n1 * 4));
+    CK(perm_out.ensure(n1 * 4));
+    CK(ix.keys_t.ensure(n1 * 4));
+    CK(ix.keys_ct.ensure(n1 * 8));
+    CK(ix.tail.ensure((size_t)K * DIM * 4));
+    CK(ix.inv_t.ensure((size_t)n_total * 4));
+    CK(cudaMemsetAsync(ix.inv_t.p, 0xff, (size_t)n_total * 4, st));
+    CK(maxbits.ensure(4));
+    for (int a = 0; a < 2; ++a) {
+        CK(ix.x[a].ensure(n1 * ROW_BYTES + 64 * ROW_BYTES));   // slack rows: tile loads may over-read nothing, but keep TMA boxes in bounds
+        CK(ix.ids[a].ensure(n1 * 4));
+        CK(ix.xnorm[a].ensure(n1 * 4));
+    }
+    cudaError_t rc = cudaSuccess;
+    auto fail = [&](cudaError_t c, const char *what) { e->err = std::string(what) + ": " + cudaGetErrorString(c); rc = c; };
+
+    if (n) {
+        k_make_keys<<<(n + 255) / 256, 256, 0, st>>>(rows, n, key_t_in.as<uint32_t>(), key_ct_in.as<uint64_t>(), perm_in.as<uint32_t>());
+        size_t tb1 = 0, tb2 = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tb1, key_t_in.as<uint32_t>(), ix.keys_t.as<uint32_t>(), perm_in.as<uint32_t>(), perm_out.as<uint32_t>(), (int)n, 0, 32, st);
+        cub::DeviceRadixSort::SortPairs(nullptr, tb2, key_ct_in.as<uint64_t>(), ix.keys_ct.as<uint64_t>(), perm_in.as<uint32_t>(), perm_out.as<uint32_t>(), (int)n, 0, 64, st);
+        cudaError_t c = tmp.ensure(tb1 > tb2 ? tb1 : tb2);
+        if (c != cudaSuccess) fail(c, "cub temp alloc");
+        const unsigned gather_blocks = (unsigned)(((size_t)n * 32 + 255) / 256);
+        if (rc == cudaSuccess) {
+            size_t tb = tmp.cap;
+            c = cub::DeviceRadixSort::SortPairs(tmp.p, tb, key_t_in.as<uint32_t>(), ix.keys_t.as<uint32_t>(), perm_in.as<uint32_t>(), perm_out.as<uint32_t>(), (int)n, 0, 32, st);
+            if (c != cudaSuccess) fail(c, "radix sort (T)");
+            k_gather<<<gather_blocks, 256, 0, st>>>(rows, perm_out.as<uint32_t>(), n, ix.id_offset, ix.x[ARENA_T].as<float>(),
+                                                     ix.ids[ARENA_T].as<uint32_t>(), ix.xnorm[ARENA_T].as<float>(), ix.inv_t.as<uint32_t>());
+        }
+        if (rc == cudaSuccess) {
+            size_t tb = tmp.cap;
+            c = cub::DeviceRadixSort::SortPairs(tmp.p, tb, key_ct_in.as<uint64_t>(), ix.keys_ct.as<uint64_t>(), perm_in.as<uint32_t>(), perm_out.as<uint32_t>(), (int)n, 0, 64, st);
+            if (c != cudaSuccess) fail(c, "radix sort (C,T)");
+            k_gather<<<gather_blocks, 256, 0, st>>>(rows, perm_out.as<uint32_t>(), n, ix.id_offset, ix.x[ARENA_CT].as<float>(),
+                                                     ix.ids[ARENA_CT].as<uint32_t>(), ix.xnorm[ARENA_CT].as<float>(), nullptr);
+        }
+        if (rc == cudaSuccess) {
+            cudaMemsetAsync(maxbits.p, 0, 4, st);
+            k_max_f32<<<296, 256, 0, st>>>(ix.xnorm[ARENA_T].as<float>(), n, maxbits.as<uint32_t>());
+        }
+    }
+    if (rc == cudaSuccess) {
+        k_tail<<<K, 128, 0, st>>>(rows, n_total, ix.tail.as<float>());
+        uint32_t bits = 0;
+        if (n) {
+            cudaError_t c = cudaMemcpyAsync(&bits, maxbits.p, 4, cudaMemcpyDeviceToHost, st);
+            if (c != cudaSuccess) fail(c, "memcpy xnorm_max");
+        }
+        cudaError_t c = cudaStreamSynchronize(st);
+        if (c != cudaSuccess) fail(c, "index build sync");
+        union { uint32_t u; float f; } cv; cv.u = bits;
+        ix.xnorm_max = cv.f;
+    }
+    if (rc == cudaSuccess) {
+        cudaError_t c = cudaGetLastError();
+        if (c != cudaSuccess) fail(c, "index build kernels");
+    }
+    key_t_in.release(); key_ct_in.release(); perm_in.release(); perm_out.release(); tmp.release(); maxbits.release();
+    if (rc != cudaSuccess) return rc;
+    if (tensor_path_available() && n) {
+        build_bf16_image(e, ARENA_T);
+        build_bf16_image(e, ARENA_CT);
+        cudaError_t c = cudaStreamSynchronize(st);
+        if (c != cudaSuccess) { e->err = std::string("bf16 image: ") + cudaGetErrorString(c); return c; }
+    }
+    ix.built = true;
+    return cudaSuccess;
+}
+
+}  // namespace hvs

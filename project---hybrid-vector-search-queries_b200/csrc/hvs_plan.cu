@@ -1,0 +1,240 @@
+// hvs_plan.cu -- K1: per-query slice lookup (device) + the query planner (host).
+//
+// Reference: the decode at include/baseline.hpp:90-93 and the four predicate scans at
+// include/baseline.hpp:107-136.  Here each predicate becomes two binary searches over the sorted
+// keys of one arena (hvs_index.cu); the planner then buckets queries that share rows into
+// 128-query tile items, or sends sparse / tiny slices to the direct scan kernel.
+#include <algorithm>
+#include <cmath>
+
+#include "hvs_engine.h"
+
+namespace hvs {
+
+template <class T>
+__device__ __forceinline__ uint32_t lower_bound_dev(const T *__restrict__ a, uint32_t n, T key)
+{   // first i with a[i] >= key
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint32_t mid = lo + ((hi - lo) >> 1);
+        if (a[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+template <class T>
+__device__ __forceinline__ uint32_t upper_bound_dev(const T *__restrict__ a, uint32_t n, T key)
+{   // first i with a[i] > key
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint32_t mid = lo + ((hi - lo) >> 1);
+        if (a[mid] <= key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// One warp per query: lane 0 decodes and searches, the warp computes ||q||^2.
+__global__ void k_plan_search(const float *__restrict__ queries, uint32_t m, const uint32_t *__restrict__ keys_t,
+                              const uint64_t *__restrict__ keys_ct, uint32_t n, QSlice *__restrict__ out)
+{
+    uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (q >= m) return;
+    const float *row = queries + (size_t)q * QROW;
+    float acc = 0.f;
+    for (int i = lane; i < DIM; i += 32) { float v = row[4 + i]; acc = fmaf(v, v, acc); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane != 0) return;
+    uint32_t type = f2u32_x86(row[0]);           // baseline.hpp:90
+    int32_t v = f2i32_x86(row[1]);               // baseline.hpp:91 (truncation toward zero)
+    float l = row[2], r = row[3];                // baseline.hpp:92-93
+    QSlice s;
+    s.arena = ARENA_T; s.begin = 0; s.end = 0; s.qnorm = acc;
+    const bool range_ok = !f32_isnan(l) && !f32_isnan(r);   // any comparison with NaN is false
+    if (type == 0) {                              // baseline.hpp:107-113: every scanned row
+        s.end = n;
+    } else if (type == 2) {                       // baseline.hpp:123-129: l <= T <= r, inclusive
+        if (range_ok) {
+            s.begin = lower_bound_dev(keys_t, n, ord_key(l));
+            s.end = upper_bound_dev(keys_t, n, ord_key(r));
+        }
+    } else if (type == 1 || type == 3) {          // baseline.hpp:114-122 / 130-136: C == (float)v
+        s.arena = ARENA_CT;
+        uint64_t kc = (uint64_t)ord_key((float)v) << 32;
+        if (type == 1) {
+            s.begin = lower_bound_dev(keys_ct, n, kc);
+            s.end = lower_bound_dev(keys_ct, n, (uint64_t)(kc + (1ull << 32)));
+        } else if (range_ok) {
+            s.begin = lower_bound_dev(keys_ct, n, (uint64_t)(kc | ord_key(l)));
+            s.end = upper_bound_dev(keys_ct, n, (uint64_t)(kc | ord_key(r)));
+        }
+    }                                             // any other type: no branch taken, empty set
+    if (s.end < s.begin) s.end = s.begin;         // l > r
+    out[q] = s;
+}
+
+cudaError_t launch_plan_search(hvs_engine *e, const float *queries_dev, uint32_t m, QSlice *slices_dev)
+{
+    if (!m) return cudaSuccess;
+    const Index &ix = e->index;
+    unsigned blocks = (unsigned)(((size_t)m * 32 + 255) / 256);
+    k_plan_search<<<blocks, 256, 0, e->stream>>>(queries_dev, m, ix.keys_t.as<uint32_t>(), ix.keys_ct.as<uint64_t>(), ix.n, slices_dev);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host planner.
+//
+// A tile item makes <= 128 queries sweep a run of arena rows together, so its cost is
+// rows x 128 pair-slots whatever the queries need; a direct scan costs exactly the rows the query
+// needs but runs at HBM speed (400 B per pair).  A query goes to the tile path when, averaged over
+// its slice, at least 128 / direct_cost_ratio other queries want the same rows.
+void plan_build(const QSlice *sl, uint32_t m, const PlanParams &pp, Plan &P)
+{
+    P = Plan();
+    std::vector<uint8_t> is_tile(m, 0);
+    uint64_t tile_qrows = 0;
+    for (uint32_t i = 0; i < m; ++i) {
+        uint32_t len = sl[i].end - sl[i].begin;
+        P.pairs += len > (uint32_t)K ? len : (uint32_t)K;
+    }
+    if (pp.mode != HVS_MODE_DIRECT) {
+        constexpr uint32_t CELL = 1024;
+        for (uint32_t a = 0; a < 2; ++a) {
+            uint32_t maxend = 0;
+            for (uint32_t i = 0; i < m; ++i)
+                if (sl[i].arena == a && sl[i].end > sl[i].begin) maxend = std::max(maxend, sl[i].end);
+            if (!maxend) continue;
+            uint32_t ncell = (maxend + CELL - 1) / CELL;
+            std::vector<int64_t> depth(ncell + 1, 0);
+            for (uint32_t i = 0; i < m; ++i)
+                if (sl[i].arena == a && sl[i].end > sl[i].begin) {
+                    depth[sl[i].begin / CELL] += 1;
+                    depth[(sl[i].end - 1) / CELL + 1] -= 1;
+                }
+            std::vector<int64_t> pref(ncell + 1, 0);   // pref[c] = sum of depth over cells < c
+            int64_t run = 0;
+            for (uint32_t c = 0; c < ncell; ++c) { run += depth[c]; pref[c + 1] = pref[c] + run; }
+            const double need = (double)QT / pp.direct_cost_ratio;
+            for (uint32_t i = 0; i < m; ++i)
+                if (sl[i].arena == a && sl[i].end > sl[i].begin) {
+                    uint32_t c0 = sl[i].begin / CELL, c1 = (sl[i].end - 1) / CELL + 1;
+                    double avg = (double)(pref[c1] - pref[c0]) / (double)(c1 - c0);
+                    if (avg >= need) { is_tile[i] = 1; tile_qrows += sl[i].end - sl[i].begin; }
+                }
+        }
+    }
+    for (uint32_t i = 0; i < m; ++i)
+        if (!is_tile[i]) { P.direct_q.push_back(i); P.pairs_computed += sl[i].end - sl[i].begin; }
+    // direct queries: neighbours in an arena share L2 lines
+    std::sort(P.direct_q.begin(), P.direct_q.end(), [&](uint32_t x, uint32_t y) {
+        if (sl[x].arena != sl[y].arena) return sl[x].arena < sl[y].arena;
+        if (sl[x].begin != sl[y].begin) return sl[x].begin < sl[y].begin;
+        return x < y;
+    });
+    if (!tile_qrows) return;
+
+    // chunk size: aim at ~16 items per SM over the whole job, power of two
+    uint64_t want = tile_qrows / ((uint64_t)QT * 16 * 148);
+    uint32_t R = 8192;
+    while ((uint64_t)R * 2 <= want && R < pp.chunk_rows * 4u) R *= 2;
+    if (R > (1u << 19)) R = 1u << 19;
+
+    struct Inc { uint32_t chunk, q; };
+    for (uint32_t a = 0; a < 2; ++a) {
+        std::vector<Inc> inc;
+        for (uint32_t i = 0; i < m; ++i)
+            if (is_tile[i] && sl[i].arena == a)
+                for (uint32_t c = sl[i].begin / R; c <= (sl[i].end - 1) / R; ++c) inc.push_back({c, i});
+        if (inc.empty()) continue;
+        std::sort(inc.begin(), inc.end(), [&](const Inc &x, const Inc &y) {
+            if (x.chunk != y.chunk) return x.chunk < y.chunk;
+            if (sl[x.q].begin != sl[y.q].begin) return sl[x.q].begin < sl[y.q].begin;
+            if (sl[x.q].end != sl[y.q].end) return sl[x.q].end < sl[y.q].end;
+            return x.q < y.q;
+        });
+        size_t p = 0;
+        while (p < inc.size()) {
+            size_t e = p;
+            while (e < inc.size() && inc[e].chunk == inc[p].chunk) ++e;
+            const uint32_t c0 = inc[p].chunk * R;
+            const uint64_t c1 = (uint64_t)c0 + R;
+            for (size_t t = p; t < e; t += QT) {
+                size_t te = std::min(e, t + (size_t)QT);
+                TileItem it{};
+                it.arena = a;
+                uint32_t lo = 0xffffffffu, hi = 0;
+                for (size_t k = t; k < te; ++k) {
+                    lo = std::min(lo, std::max(sl[inc[k].q].begin, c0));
+                    hi = std::max(hi, (uint32_t)std::min<uint64_t>(sl[inc[k].q].end, c1));
+                }
+                it.row_begin = lo; it.row_end = hi;
+                it.nq = (uint32_t)(te - t);
+                it.q_off = (uint32_t)P.item_q.size();
+                for (size_t k = t; k < te; ++k) P.item_q.push_back(inc[k].q);
+                uint32_t rows = hi - lo;
+                bool tensor = false;
+                if (pp.tensor_available) {
+                    if (pp.mode == HVS_MODE_TENSOR) tensor = true;
+                    else if (pp.mode == HVS_MODE_AUTO) tensor = rows >= pp.tensor_min_rows && it.nq >= pp.tensor_min_q;
+                }
+                it.kind = tensor ? 1u : 0u;
+                P.items.push_back(it);
+                P.pairs_computed += (uint64_t)rows * it.nq;
+            }
+            p = e;
+        }
+    }
+    // longest first (LPT) within each kernel kind; equal-cost items stay in (arena,row) order so
+    // CTAs running concurrently share the same X chunk in L2
+    std::stable_sort(P.items.begin(), P.items.end(), [](const TileItem &x, const TileItem &y) {
+        if (x.kind != y.kind) return x.kind < y.kind;
+        return (x.row_end - x.row_begin) > (y.row_end - y.row_begin);
+    });
+    // candidate lists: item-major after sorting
+    std::vector<std::vector<uint32_t>> lists_of(m);
+    uint32_t off = 0;
+    for (auto &it : P.items) {
+        it.out_off = off;
+        for (uint32_t s = 0; s < it.nq; ++s) lists_of[P.item_q[it.q_off + s]].push_back(off + s);
+        off += it.nq;
+        if (it.kind) ++P.n_tensor; else ++P.n_ffma;
+    }
+    P.n_lists = off;
+    P.q_list_off.push_back(0);
+    for (uint32_t i = 0; i < m; ++i)
+        if (is_tile[i]) {
+            P.tile_q.push_back(i);
+            for (uint32_t l : lists_of[i]) P.q_lists.push_back(l);
+            P.q_list_off.push_back((uint32_t)P.q_lists.size());
+        }
+}
+
+}  // namespace hvs
+
+extern "C" int hvs_plan_dryrun(const uint32_t *arena, const uint32_t *begin, const uint32_t *end, uint32_t m,
+                               uint32_t mode, uint8_t *out_kind, uint32_t *out_items, uint32_t max_items,
+                               uint64_t *out_pairs_computed)
+{
+    if ((!arena || !begin || !end || !out_kind) && m) return HVS_ERR_INVALID;
+    std::vector<hvs::QSlice> sl(m);
+    for (uint32_t i = 0; i < m; ++i) {
+        if (arena[i] > 1 || end[i] < begin[i]) return HVS_ERR_INVALID;
+        sl[i].arena = arena[i]; sl[i].begin = begin[i]; sl[i].end = end[i]; sl[i].qnorm = 0.f;
+    }
+    hvs::PlanParams pp;
+    pp.mode = mode;
+    pp.tensor_available = (mode == HVS_MODE_TENSOR || mode == HVS_MODE_AUTO);
+    hvs::Plan P;
+    hvs::plan_build(sl.data(), m, pp, P);
+    for (uint32_t i = 0; i < m; ++i) out_kind[i] = 1;
+    for (uint32_t q : P.direct_q) out_kind[q] = 0;
+    if (out_items)
+        for (size_t k = 0; k < P.items.size() && k < max_items; ++k) {
+            out_items[4 * k + 0] = P.items[k].arena;
+            out_items[4 * k + 1] = P.items[k].row_begin;
+            out_items[4 * k + 2] = P.items[k].row_end;
+            out_items[4 * k + 3] = P.items[k].nq | (P.items[k].kind << 16);
+        }
+    if (out_pairs_computed) *out_pairs_computed = P.pairs_computed;
+    return (int)P.items.size();
+}

@@ -1,0 +1,177 @@
+// hvs_topk.cuh -- block-level selection primitives shared by the direct scan (K4), the finalize
+// kernel (K5) and the merge kernel.  Candidates are 64-bit keys (distance bits << 32 | payload):
+// distances are sums of squares (>= 0) so the unsigned integer order of the key is the order
+// "closer first, smaller payload first on ties".
+//
+// Reference: this replaces class Knn of include/optimized_impl.h:179-438 (unsorted 100-slot array,
+// replace-the-worst in check_add :284-335, arg-max rescan in find_worst :201-274, final std::sort
+// in get_knn_sorted :392-437).  Instead of rescanning 100 slots per accepted candidate, accepted
+// candidates are appended to a buffer that is compacted (bitonic sort, keep the best 100) only when
+// it fills; between compactions the acceptance test is one compare against a stale threshold.
+#pragma once
+#include "hvs_common.cuh"
+
+namespace hvs {
+
+constexpr uint64_t KEY_INF = 0xffffffffffffffffull;
+
+// In-place ascending bitonic sort of a[0..n) in shared memory, n a power of two, all `nthreads`
+// threads of the block participate.  Ends with a __syncthreads().
+__device__ __forceinline__ void block_bitonic_sort(uint64_t *a, int n, int tid, int nthreads)
+{
+    for (int k = 2; k <= n; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < n; i += nthreads) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    uint64_t x = a[i], y = a[ixj];
+                    bool up = (i & k) == 0;
+                    if ((x > y) == up) { a[i] = y; a[ixj] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// In-place ascending bitonic sort of a[0..n) in shared memory by ONE warp, n a power of two >= 2.
+__device__ __forceinline__ void warp_bitonic_sort(uint64_t *a, int n, int lane)
+{
+    for (int k = 2; k <= n; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = lane; t < (n >> 1); t += 32) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int ixj = i | j;
+                const uint64_t x = a[i], y = a[ixj];
+                const bool up = (i & k) == 0;
+                if ((x > y) == up) { a[i] = y; a[ixj] = x; }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// Order-preserving float <-> uint32 for scores that may be negative (s = ||x||^2 - 2 q.x).
+__device__ __forceinline__ uint32_t okey(float s)
+{
+    const uint32_t u = __float_as_uint(s);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float okey_inv(uint32_t k)
+{
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+__device__ __forceinline__ int next_pow2(int v)
+{
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+// Streaming top-K buffer in shared memory, one per CTA (one query per CTA).
+//   accept test : key_dist < thr           (thr = +inf until the first compaction)
+//   compaction  : sort, keep the K best plus every entry within `margin` of the K-th
+// With margin == 0 and exact distances this is an exact top-K; with margin = 2*eps and approximate
+// distances it keeps a superset that provably contains the exact top-K (DESIGN.md "margins").
+//   ORD == false : key = raw bits of a non-negative distance   (pack_key)
+//   ORD == true  : key = okey(score), scores of either sign
+template <int CAP, bool ORD = false>
+struct TopBuf {
+    uint64_t cand[CAP];
+    uint32_t cnt;
+    float thr;
+    uint32_t overflow;   // set when the margin set alone exceeds the buffer
+
+    __device__ __forceinline__ void init(int tid)
+    {
+        if (tid == 0) { cnt = 0; thr = __int_as_float(0x7f800000); overflow = 0; }
+    }
+    static __device__ __forceinline__ float key_val(uint64_t k)
+    {
+        return ORD ? okey_inv((uint32_t)(k >> 32)) : __uint_as_float((uint32_t)(k >> 32));
+    }
+    __device__ __forceinline__ void push(float d, uint32_t payload)
+    {
+        uint32_t slot = atomicAdd(&cnt, 1u);
+        if (slot < (uint32_t)CAP) cand[slot] = ORD ? (((uint64_t)okey(d) << 32) | payload) : pack_key(d, payload);
+    }
+    // Call from ALL threads after a __syncthreads().  Keeps <= keep_max entries.
+    __device__ __forceinline__ void compact(int tid, int nthreads, float margin, int keep_max)
+    {
+        int c = min((int)cnt, CAP);
+        int n = next_pow2(c < 2 ? 2 : c);
+        for (int i = c + tid; i < n; i += nthreads) cand[i] = KEY_INF;
+        __syncthreads();
+        block_bitonic_sort(cand, n, tid, nthreads);
+        if (c > K) {
+            float dk = key_val(cand[K - 1]);
+            float lim = dk + margin;
+            // entries are sorted: count those with dist <= lim (all of the first K qualify)
+            int keep = K;
+            if (margin > 0.f) {
+                // every thread scans a strided share; tiny (CAP <= 1024)
+                __shared__ int s_keep;
+                if (tid == 0) s_keep = K;
+                __syncthreads();
+                int local = 0;
+                for (int i = K + tid; i < c; i += nthreads)
+                    if (key_val(cand[i]) <= lim) local = i + 1;
+                if (local) atomicMax(&s_keep, local);
+                __syncthreads();
+                keep = s_keep;
+            }
+            if (keep > keep_max) { keep = keep_max; if (tid == 0) overflow = 1; }
+            __syncthreads();
+            if (tid == 0) { cnt = keep; thr = (margin > 0.f) ? nextafterf(lim, __int_as_float(0x7f800000)) : dk; }
+        } else if (tid == 0) {
+            cnt = c;
+        }
+        __syncthreads();
+    }
+};
+
+// Final stage shared with K5: `top.cand[0..cnt)` hold (dist, arena_pos); convert to (dist, id),
+// apply the pad rule, sort, write.
+template <int CAP, bool ORD>
+__device__ __forceinline__ void finish_query(TopBuf<CAP, ORD> &top, const float *q_smem, const Arena &A, uint32_t len,
+                                             const float *__restrict__ tail, uint32_t n_total, uint32_t q, bool partial,
+                                             uint32_t *__restrict__ out_ids, float *__restrict__ out_dist,
+                                             uint32_t *__restrict__ out_count, int tid, int nthreads)
+{
+    // keep the best K by (dist, pos), then re-key by original id so the output order is
+    // (dist, id) -- deterministic whatever path produced the candidates
+    if ((int)top.cnt > K) top.compact(tid, nthreads, 0.f, K);
+    int c = min((int)top.cnt, K);
+    for (int i = tid; i < c; i += nthreads) {
+        uint64_t k = top.cand[i];
+        top.cand[i] = (k & 0xffffffff00000000ull) | A.ids[(uint32_t)k];
+    }
+    __syncthreads();
+    if (!partial && len < (uint32_t)K) {
+        // include/baseline.hpp:138-147: append ids n-1, n-2, ... (no predicate, no de-duplication)
+        // until there are K candidates; they are ranked together with the real matches.
+        int npad = K - (int)len;
+        for (int s = tid; s < npad; s += nthreads) {
+            float d = ref_dist_row(tail + (size_t)s * DIM, q_smem);
+            top.cand[c + s] = pack_key(d, n_total - 1u - (uint32_t)s);
+        }
+        c += npad;
+    }
+    for (int i = c + tid; i < 128; i += nthreads) top.cand[i] = KEY_INF;
+    __syncthreads();
+    block_bitonic_sort(top.cand, 128, tid, nthreads);
+    if (!partial) {
+        for (int i = tid; i < K; i += nthreads) out_ids[(size_t)q * K + i] = (uint32_t)top.cand[i];
+    } else {
+        for (int i = tid; i < K; i += nthreads) {
+            uint64_t k = top.cand[i];
+            bool valid = i < c;
+            out_ids[(size_t)q * K + i] = valid ? (uint32_t)k : 0xffffffffu;
+            out_dist[(size_t)q * K + i] = valid ? __uint_as_float((uint32_t)(k >> 32)) : __int_as_float(0x7f800000);
+        }
+        if (tid == 0) out_count[q] = len;
+    }
+}
+
+}  // namespace hvs
