@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py -- queries/sec of the filtered k-NN solve step (BASELINE.json metric).
+
+A "step" is one pass of the hot path -- hvs_solve over the whole query batch -- against an index
+that was built once before the timed region (the contest's indexing phase never sees queries).
+  value : queries/s with the query batch already resident in HBM (hvs_solve_device), CUDA events
+          on the engine's stream (which is torch's current stream), max over ranks.
+  e2e   : the same through the host entry point hvs_solve: pinned host queries -> H2D -> solve ->
+          D2H of the uint32 ids, every step.
+Workload at N=1: BASELINE.json configs[2], D=10^7, Q=4x10^4 mixed types 0-3 (synthetic, the repo's
+seedable generator with the reference generators' value ranges and integer categories).
+N>1: query-sharded, D replicated, no data-path collective: each rank solves its own Q-sized batch
+(weak scaling).  `--variant data` runs the data-sharded comparison (NCCL all-gather + K5 merge).
+`--impl reference` times the reference's own CPU vec_query (oracle/_ref) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+PKG = "project---hybrid-vector-search-queries_b200"
+
+WORKLOADS = {
+    # name: (N, M, ncat, types, range_width)
+    "default": (10_000, 100, 10, (0, 1, 2, 3), None),                # configs[0]
+    "medium": (1_000_000, 10_000, 100, (0, 1, 2, 3), None),          # configs[1]
+    "large": (10_000_000, 40_000, 100, (0, 1, 2, 3), None),          # configs[2]  <- the metric's config
+    "type0": (10_000_000, 40_000, 100, (0,), None),                  # configs[3]
+    "selective": (10_000_000, 40_000, 1000, (3,), 0.06),             # configs[4]
+}
+DATA_SEED, QUERY_SEED = 3, 4
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="large", choices=sorted(WORKLOADS))
+    ap.add_argument("--mode", default="auto", choices=["auto", "exact", "direct", "tensor"])
+    ap.add_argument("--variant", default="query", choices=["query", "data"], help="multi-GPU sharding")
+    ap.add_argument("--cpu-sample", type=int, default=32, help="queries of the workload timed on the CPU baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    return ap.parse_args()
+
+
+def make_inputs(hvs, wl, rank=0):
+    n, m, ncat, types, rw = WORKLOADS[wl]
+    d = hvs.gen_data(n, DATA_SEED, ncat=ncat)
+    q = hvs.gen_queries(m, QUERY_SEED + 1000 * rank, ncat=ncat, types=types, range_width=rw)
+    return d, q
+
+
+# ---- clocks -----------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.path = tempfile.mktemp(prefix="hvs_clocks_", suffix=".csv")
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1])); pw.append(float(p[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---- the reference arm / CPU baseline ------------------------------------------------------------
+def cpu_reference_run(d, q_sample, steps, warmup):
+    """Times the reference's own vec_query on the host cores.  Returns (best-variant dict, all)."""
+    from oracle import oracle as O
+    cores = os.cpu_count() or 1
+    out = {}
+    order = [("parallel_nodbg", "reference", "optimized_parallel.hpp (IMPL=3) with its ENABLE_PERF_DBG switch set to 0"),
+             ("parallel", "reference", "optimized_parallel.hpp (IMPL=3) exactly as shipped")]
+    for impl, kind, desc in order:
+        if not O.ref_available(impl):
+            continue
+        ts = []
+        for s in range(warmup + steps):
+            _, secs = O.ref_vec_query(impl, d, q_sample)
+            if s >= warmup:
+                ts.append(secs)
+        out[impl] = {"kind": kind, "desc": desc, "secs": float(np.mean(ts)), "threads": min(cores, max(1, d.shape[0] // 100_000))}
+        if impl == "parallel_nodbg":
+            break           # the as-shipped build is strictly slower; time it only if the fair one is absent
+    if not out:            # reference not compiled here: the oracle port (scalar, 1 thread)
+        ts = []
+        for s in range(warmup + steps):
+            t0 = time.perf_counter()
+            O.vec_query(d, q_sample, want_dist=False)
+            if s >= warmup:
+                ts.append(time.perf_counter() - t0)
+        out["port"] = {"kind": "port", "desc": "oracle/hvs_oracle.c restatement of baseline.hpp", "secs": float(np.mean(ts)), "threads": 1}
+    best = min(out.values(), key=lambda v: v["secs"])
+    return best, out
+
+
+def sample_queries(q, k):
+    """A bounded sample with the workload's own type mix: every (M/k)-th query."""
+    idx = np.linspace(0, q.shape[0] - 1, min(k, q.shape[0])).astype(np.int64)
+    return np.ascontiguousarray(q[idx]), idx
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    hvs_dg = importlib.import_module(PKG + ".datagen")
+    n, m, ncat, types, rw = WORKLOADS[args.workload]
+    d = hvs_dg.gen_data(n, DATA_SEED, ncat=ncat)
+    q = hvs_dg.gen_queries(m, QUERY_SEED, ncat=ncat, types=types, range_width=rw)
+    qs, _ = sample_queries(q, args.cpu_sample)
+    best, allv = cpu_reference_run(d, qs, args.steps, args.warmup)
+    qps = qs.shape[0] / best["secs"]
+    line = {"impl": "reference", "metric": "queries/sec", "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": best["secs"] * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, 1),
+            "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": best["threads"], "kind": best["kind"],
+                             "sample": f"{qs.shape[0]} of the workload's {m} queries (every {m // max(1, qs.shape[0])}-th, same type mix) "
+                                       f"against the full D={n}; {best['desc']}; host has {os.cpu_count()} cores",
+                             "variants": {k: {"secs_per_step": v["secs"], "threads": v["threads"]} for k, v in allv.items()}},
+            "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    n, m, ncat, types, rw = WORKLOADS[args.workload]
+    return {"workload": f"{args.workload}: D={n} rows x 100-d f32, Q={m} queries per GPU, k=100, types {list(types)} uniform, "
+                        f"{ncat} integer categories" + (f", range width {rw}" if rw else ""),
+            "D": n, "Q_per_gpu": m, "k": 100, "dim": 100, "ncat": ncat, "types": list(types), "mode": args.mode,
+            "sharding": ("query-sharded, D replicated" if args.variant == "query" else "data-sharded, NCCL all-gather + merge") if world > 1 else "single GPU",
+            "l2": "inputs larger than L2 (two 4 GB arenas swept per step); no explicit flush"}
+
+
+# ---- the B200 arm ---------------------------------------------------------------------------------
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    hvs = importlib.import_module(PKG)
+    hvs.lib()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    mode = {"auto": hvs.MODE_AUTO, "exact": hvs.MODE_EXACT, "direct": hvs.MODE_DIRECT, "tensor": hvs.MODE_TENSOR}[args.mode]
+    n, m, ncat, types, rw = WORKLOADS[args.workload]
+    d, q = make_inputs(hvs, args.workload, rank if args.variant == "query" else 0)
+    stream = torch.cuda.current_stream()
+    data_sharded = world > 1 and args.variant == "data"
+    if data_sharded:
+        lo, hi = rank * n // world, (rank + 1) * n // world
+        eng = hvs.Engine(device=local_rank, mode=mode, stream=stream.cuda_stream, id_offset=lo)
+        eng.index_build(d[lo:hi])
+    else:
+        eng = hvs.Engine(device=local_rank, mode=mode, stream=stream.cuda_stream)
+        eng.index_build(d)
+    st_index = eng.stats()
+
+    q_pinned = torch.from_numpy(q).pin_memory()
+    out_pinned = torch.empty((m, 100), dtype=torch.int32).pin_memory()
+    q_dev = q_pinned.cuda(non_blocking=True)
+    out_dev = torch.empty((m, 100), dtype=torch.int32, device="cuda")
+    if data_sharded:
+        p_dist = torch.empty((m, 100), dtype=torch.float32, device="cuda")
+        p_ids = torch.empty((m, 100), dtype=torch.int32, device="cuda")
+        p_cnt = torch.empty((m,), dtype=torch.int32, device="cuda")
+        g_dist = torch.empty((world, m, 100), dtype=torch.float32, device="cuda")
+        g_ids = torch.empty((world, m, 100), dtype=torch.int32, device="cuda")
+        g_cnt = torch.empty((world, m), dtype=torch.int32, device="cuda")
+        tail = torch.from_numpy(np.ascontiguousarray(d[n - 100:])).cuda()
+    torch.cuda.synchronize()
+
+    def step_device():
+        if data_sharded:
+            eng.solve_partial_device(q_dev, p_dist, p_ids, p_cnt)
+            dist.all_gather_into_tensor(g_dist, p_dist)
+            dist.all_gather_into_tensor(g_ids, p_ids)
+            dist.all_gather_into_tensor(g_cnt, p_cnt)
+            eng.merge_partials_device(q_dev, world, g_dist, g_ids, g_cnt, tail, n, out_dev)
+        else:
+            eng.solve_device(q_dev, out_dev)
+
+    def step_host():
+        eng.solve(q_pinned.numpy(), out_pinned.numpy().view(np.uint32))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        agg = {}
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+            s = eng.stats()
+            for k, v in s.items():
+                agg[k] = agg.get(k, 0) + v
+        e1.record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = e0.elapsed_time(e1)
+        ms = max(ms, 0.0)
+        t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1]), {k: v / steps for k, v in agg.items()}
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms_dev, wall_dev, st = timed(step_device, args.steps, args.warmup)
+    clocks = sampler.stop() if sampler else None
+    ids_dev = out_dev.cpu().numpy().view(np.uint32).copy()
+    if data_sharded:
+        e2e = None
+    else:
+        ms_host, wall_host, st_host = timed(step_host, max(1, args.steps), 1)
+        assert np.array_equal(out_pinned.numpy().view(np.uint32), ids_dev), "host and device entry points disagree"
+        # host-side stalls (planner) do not show on the stream: use the larger of event time and wall clock
+        e2e_ms = max(ms_host, wall_host) / max(1, args.steps)
+        e2e = {"value": world * m / (e2e_ms * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": int(q_pinned.numel() * 4), "d2h_bytes_per_step": int(out_pinned.numel() * 4),
+               "ms_h2d": st_host["ms_h2d"], "ms_d2h": st_host["ms_d2h"], "entry_point": "hvs_solve (pinned host buffers)"}
+    ms_step = max(ms_dev, wall_dev) / args.steps
+
+    peak_tf, peak_mhz = eng.measure_ffma_peak(3)
+    if rank != 0:
+        eng.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (per launch == per step: one launch of each kernel per solve)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    kern = {"K2 k_tile_ffma": st["ms_tile_ffma"], "K3 k_tile_tensor": st["ms_tile_tensor"], "K4 k_direct": st["ms_direct"],
+            "K5 k_finalize": st["ms_finalize"], "K1 plan": st["ms_plan"]}
+    dom = max(kern, key=kern.get)
+    flops_tile = 200.0 * st["pairs_tile"]              # 200 flop per (query,row) pair
+    rl_ffma = None
+    if st["ms_tile_ffma"] > 0:
+        a = flops_tile / (st["ms_tile_ffma"] * 1e-3) / 1e12
+        rl_ffma = {"kernel": "k_tile_ffma", "bound": "fp32", "achieved": a, "peak": peak_tf, "unit": "TFLOP/s", "frac": a / peak_tf,
+                   "peak_source": f"FFMA microkernel measured in this run at {peak_mhz:.0f} MHz (MEASURED_PEAKS.json has no FP32 figure); "
+                                  f"nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.5", "frac_of_nominal": a / 74.5,
+                   "traffic": None, "algorithmic_flop_per_launch": flops_tile, "ms_per_launch": st["ms_tile_ffma"]}
+    rl_direct = None
+    if st["ms_direct"] > 0:
+        b = 400.0 * st["pairs_direct"]                  # B_pair: 400 B per pair, no reuse
+        a = b / (st["ms_direct"] * 1e-3) / 1e9
+        rl_direct = {"kernel": "k_direct", "bound": "hbm", "achieved": a, "peak": hbm_peak, "unit": "GB/s", "frac": a / hbm_peak,
+                     "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({hbm_src})", "traffic": None,
+                     "algorithmic_bytes_per_launch": b, "ms_per_launch": st["ms_direct"]}
+    roofline = rl_ffma if dom.startswith("K2") or rl_direct is None else rl_direct
+    if dom.startswith("K4") and rl_direct:
+        roofline = rl_direct
+    others = [r for r in (rl_ffma, rl_direct) if r is not None and r is not roofline]
+
+    line = {"metric": "queries/sec", "value": world * m / (ms_step * 1e-3), "unit": "queries/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(round(st["launches"] * args.steps)),
+            "roofline": roofline, "roofline_other": others, "dominant_kernel": dom,
+            "kernel_ms_per_step": kern,
+            "stats": {k: st[k] for k in ("pairs", "pairs_tile", "pairs_direct", "pairs_computed", "n_direct", "n_tile",
+                                         "n_items_ffma", "n_items_tensor", "n_fallback", "launches", "ms_solve_device")},
+            "index_build_ms": st_index["ms_index_build"],
+            "alg_tflops_whole_step": 200.0 * st["pairs"] / (ms_step * 1e-3) / 1e12}
+
+    # ---- parity on a sample, outside the timed region (the oracle is the checker, never the thing measured)
+    if not args.no_parity and not data_sharded:
+        from oracle import check, oracle as O
+        pick = np.linspace(0, m - 1, 8).astype(np.int64)
+        t0 = time.perf_counter()
+        if O.ref_available("parallel_nodbg") and n >= 1_000_000:
+            ref, _ = O.ref_vec_query("parallel_nodbg", d, q[pick])
+            who = "reference optimized_parallel (oracle/_ref)"
+        else:
+            ref = O.vec_query(d, q[pick], want_dist=False)
+            who = "oracle port of baseline.hpp"
+        p = check.compare(d, q[pick], ref, ids_dev[pick], rtol=1e-4 if "optimized" in who else 1e-5)
+        line["parity"] = {"against": who, "queries": int(len(pick)), "ok": bool(p.ok), "recall_at_100": p.recall_mean,
+                          "max_rel_dist_err": p.max_rel, "secs": time.perf_counter() - t0}
+    if not args.no_cpu_baseline:
+        qs, _ = sample_queries(q, args.cpu_sample)
+        best, allv = cpu_reference_run(d, qs, 1, 0)
+        line["cpu_baseline"] = {"value": qs.shape[0] / best["secs"], "unit": "queries/s", "cores": best["threads"],
+                                "kind": best["kind"],
+                                "sample": f"{qs.shape[0]} of the {m} queries (every {m // max(1, qs.shape[0])}-th, same type mix) against the "
+                                          f"full D={n}, one pass; {best['desc']}; host has {os.cpu_count()} cores"}
+    print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under it so that there is one process per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

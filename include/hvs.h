@@ -96,6 +96,8 @@ typedef struct hvs_stats {
     float ms_d2h;               /* result download (host entry points only) */
     float ms_solve_device;      /* plan .. finalize, device time */
     float ms_solve_wall;        /* whole call, host wall clock */
+    uint64_t pairs_tile;        /* share of `pairs` that belongs to queries solved by tile sweeps */
+    uint64_t pairs_direct;      /* share of `pairs` that belongs to queries solved by the direct scan */
 } hvs_stats;
 
 HVS_API uint32_t hvs_abi_version(void);

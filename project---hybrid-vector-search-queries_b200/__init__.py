@@ -59,7 +59,7 @@ class Stats(C.Structure):
                 ("ms_index_build", C.c_float), ("ms_h2d", C.c_float), ("ms_plan", C.c_float), ("ms_direct", C.c_float),
                 ("ms_tile", C.c_float), ("ms_tile_ffma", C.c_float), ("ms_tile_tensor", C.c_float),
                 ("ms_finalize", C.c_float), ("ms_d2h", C.c_float), ("ms_solve_device", C.c_float),
-                ("ms_solve_wall", C.c_float)]
+                ("ms_solve_wall", C.c_float), ("pairs_tile", C.c_uint64), ("pairs_direct", C.c_uint64)]
 
     def as_dict(self) -> dict:
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "struct_size"}

@@ -160,7 +160,7 @@ static int solve_impl(hvs_engine *e, const float *q_dev, uint32_t m, bool partia
 {
     hvs_stats &st = e->stats;
     st.m = m;
-    st.pairs = st.pairs_computed = st.rows_union = 0;
+    st.pairs = st.pairs_computed = st.rows_union = st.pairs_tile = st.pairs_direct = 0;
     st.n_direct = st.n_tile = st.n_items_ffma = st.n_items_tensor = st.n_fallback = st.launches = 0;
     st.ms_plan = st.ms_direct = st.ms_tile = st.ms_tile_ffma = st.ms_tile_tensor = st.ms_finalize = st.ms_solve_device = 0.f;
     if (!m) return HVS_OK;
@@ -182,6 +182,8 @@ static int solve_impl(hvs_engine *e, const float *q_dev, uint32_t m, bool partia
     plan_build(e->h_slices.as<QSlice>(), m, pp, P);
     st.pairs = P.pairs;
     st.pairs_computed = P.pairs_computed;
+    st.pairs_tile = P.pairs_tile;
+    st.pairs_direct = P.pairs - P.pairs_tile;
     st.n_direct = (uint32_t)P.direct_q.size();
     st.n_tile = (uint32_t)P.tile_q.size();
     st.n_items_ffma = P.n_ffma;

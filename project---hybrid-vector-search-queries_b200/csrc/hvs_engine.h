@@ -91,7 +91,7 @@ struct Plan {
     std::vector<uint32_t> tile_q;         // queries that go through finalize
     std::vector<uint32_t> q_list_off;     // CSR over tile_q: lists of each tile query  [tile_q.size()+1]
     std::vector<uint32_t> q_lists;        // candidate-list indices
-    uint64_t pairs = 0, pairs_computed = 0;
+    uint64_t pairs = 0, pairs_computed = 0, pairs_tile = 0;
     uint32_t n_lists = 0;
     uint32_t n_ffma = 0, n_tensor = 0;
 };

@@ -119,7 +119,11 @@ void plan_build(const QSlice *sl, uint32_t m, const PlanParams &pp, Plan &P)
                 if (sl[i].arena == a && sl[i].end > sl[i].begin) {
                     uint32_t c0 = sl[i].begin / CELL, c1 = (sl[i].end - 1) / CELL + 1;
                     double avg = (double)(pref[c1] - pref[c0]) / (double)(c1 - c0);
-                    if (avg >= need) { is_tile[i] = 1; tile_qrows += sl[i].end - sl[i].begin; }
+                    if (avg >= need) {
+                        is_tile[i] = 1;
+                        tile_qrows += sl[i].end - sl[i].begin;
+                        P.pairs_tile += std::max(sl[i].end - sl[i].begin, (uint32_t)K);
+                    }
                 }
         }
     }

@@ -128,7 +128,8 @@ k_tile_ffma(const float *__restrict__ queries, const QSlice *__restrict__ slices
             atomicMin(&S.hi_min, hi);
         }
         S.qid[tid] = id; S.qlo[tid] = lo; S.qhi[tid] = hi; S.margin[tid] = mg;
-        S.thr[tid] = __int_as_float(0x7f800000);
+        // unused query slots of a short item must never accept a row (nobody merges their buffers)
+        S.thr[tid] = __int_as_float((uint32_t)tid < it.nq ? 0x7f800000 : 0xff800000);
         S.bcnt[tid] = 0; S.lcnt[tid] = 0;
     }
     for (int idx = tid; idx < TQ * (DIM / 4); idx += NT) {

@@ -45,3 +45,4 @@ if __name__ == "__main__":
     run(1_000_000, 4096, 100, M, check_n=16)
     run(1_000_000, 10_000, 100, [("exact", hvs.MODE_EXACT)], check_n=8)
     run(4_000_000, 8192, 100, [("exact", hvs.MODE_EXACT)], types=(0,), check_n=4)
+    run(10_000_000, 40_000, 100, [("exact", hvs.MODE_EXACT)], check_n=0, reps=1)
