@@ -99,7 +99,7 @@ extern "C" void hvs_destroy(hvs_engine *e)
     for (int a = 0; a < 2; ++a) { ix.x[a].release(); ix.ids[a].release(); ix.xnorm[a].release(); ix.xb[a].release(); }
     ix.keys_t.release(); ix.keys_ct.release(); ix.tail.release(); ix.inv_t.release();
     DevBuf *bufs[] = {&e->d_queries, &e->d_out, &e->d_slices, &e->d_direct_q, &e->d_items, &e->d_item_q, &e->d_tile_q,
-                      &e->d_qoff, &e->d_qlists, &e->d_cand, &e->d_cand_cnt, &e->d_scratch, &e->d_flags,
+                      &e->d_qoff, &e->d_qlists, &e->d_cand, &e->d_cand_cnt, &e->d_scratch, &e->d_flags, &e->d_gthr,
                       &e->d_work_counter, &e->d_rescore_ids, &e->d_rescore_out};
     for (DevBuf *b : bufs) b->release();
     e->h_slices.release(); e->h_stage.release();
@@ -225,17 +225,21 @@ static int solve_impl(hvs_engine *e, const float *q_dev, uint32_t m, bool partia
         ECUDA(e->d_cand_cnt.ensure((size_t)P.n_lists * 4));
         ECUDA(e->d_flags.ensure((size_t)m * 4));
         ECUDA(cudaMemsetAsync(e->d_flags.p, 0, (size_t)m * 4, s));
+        ECUDA(e->d_gthr.ensure((size_t)m * 4));
+        ECUDA(launch_fill_u32(e, e->d_gthr.as<uint32_t>(), 0xff800000u /* okey(+inf) */, m));
         const TileItem *d_items = e->d_items.as<TileItem>();
         cudaEventRecord(e->ev[5], s);
+        if (P.n_ffma && P.n_tensor) EFAIL(HVS_ERR_STATE, "planner mixed FFMA and tensor items in one solve");
         if (P.n_ffma) {
             ECUDA(launch_tile_ffma(e, q_dev, d_sl, d_items, 0, P.n_ffma, e->d_item_q.as<uint32_t>(), e->d_cand.as<uint64_t>(),
-                                   e->d_cand_cnt.as<uint32_t>(), e->d_flags.as<uint32_t>(), 1.0f));
+                                   e->d_cand_cnt.as<uint32_t>(), e->d_gthr.as<uint32_t>(), e->d_flags.as<uint32_t>(), 1.0f));
             st.launches++;
         }
         cudaEventRecord(e->ev[6], s);
         if (P.n_tensor) {
-            ECUDA(launch_tile_tensor(e, q_dev, d_sl, d_items, P.n_ffma, P.n_tensor, e->d_item_q.as<uint32_t>(),
-                                     e->d_cand.as<uint64_t>(), e->d_cand_cnt.as<uint32_t>(), e->d_flags.as<uint32_t>()));
+            ECUDA(launch_tile_tensor(e, q_dev, d_sl, d_items, 0, P.n_tensor, e->d_item_q.as<uint32_t>(),
+                                     e->d_cand.as<uint64_t>(), e->d_cand_cnt.as<uint32_t>(), e->d_gthr.as<uint32_t>(),
+                                     e->d_flags.as<uint32_t>()));
             st.launches++;
         }
         cudaEventRecord(e->ev[7], s);

@@ -70,14 +70,15 @@ struct Index {
 };
 
 // ---- tile work items (K2 / K3) ----------------------------------------------------------------
-constexpr int QT = 128;        // queries per tile item
-constexpr int KOUT = 128;      // candidates an item hands to finalize per query (<= this many)
+constexpr int QT = 128;          // queries per FFMA tile item (K2)
+constexpr int QT_TENSOR = 256;   // queries per tensor tile item (K3): two M=128 halves share every data stage
+constexpr int KOUT = 256;        // candidates an item hands to finalize per query (<= this many)
 
 struct TileItem {              // one CTA-sized unit of work: <= 128 queries sweep arena rows [row_begin,row_end)
     uint32_t arena;
     uint32_t row_begin;
     uint32_t row_end;
-    uint32_t nq;               // 1..128
+    uint32_t nq;               // 1..128 (FFMA) or 1..256 (tensor)
     uint32_t q_off;            // offset into the item-query list (item_q[q_off .. q_off+nq))
     uint32_t out_off;          // first candidate-list index of this item (list = out_off + slot)
     uint32_t kind;             // 0 = FFMA, 1 = tensor
@@ -99,9 +100,9 @@ struct Plan {
 struct PlanParams {
     uint32_t mode = HVS_MODE_AUTO;
     uint32_t chunk_rows = 1u << 17;       // max rows an item sweeps
-    uint32_t tensor_min_rows = 1u << 14;  // AUTO: items at least this long with >= tensor_min_q queries use K3
-    uint32_t tensor_min_q = 32;
-    double direct_cost_ratio = 12.0;      // tile pair vs direct pair throughput ratio
+    uint32_t min_tile_len = 1024;         // shorter slices always take the direct scan
+    double direct_cost_ratio = 12.0;      // FFMA tile pair-slot vs direct pair throughput ratio
+    double tensor_min_depth = 0.75;       // tensor items: average queries per row needed (the sweep is bandwidth-, not slot-priced)
     bool tensor_available = false;
 };
 
@@ -121,7 +122,7 @@ struct hvs_engine {
     hvs_stats stats{};
     // per-solve scratch (grow-only)
     hvs::DevBuf d_queries, d_out, d_slices, d_direct_q, d_items, d_item_q, d_tile_q, d_qoff, d_qlists;
-    hvs::DevBuf d_cand, d_cand_cnt, d_scratch, d_flags, d_work_counter, d_rescore_ids, d_rescore_out;
+    hvs::DevBuf d_cand, d_cand_cnt, d_scratch, d_flags, d_gthr, d_work_counter, d_rescore_ids, d_rescore_out;
     hvs::HostPinned h_slices, h_stage;
     cudaEvent_t ev[12]{};
     hvs::Plan plan;
@@ -140,11 +141,12 @@ cudaError_t launch_direct(hvs_engine *e, const float *queries_dev, const QSlice 
 cudaError_t launch_tile_ffma(hvs_engine *e, const float *queries_dev, const QSlice *slices_dev,
                              const TileItem *items_dev, uint32_t item_begin, uint32_t n_items,
                              const uint32_t *item_q_dev, uint64_t *cand_dev, uint32_t *cand_cnt_dev,
-                             uint32_t *flags_dev, float margin_scale);
+                             uint32_t *gthr_dev, uint32_t *flags_dev, float margin_scale);
 cudaError_t launch_tile_tensor(hvs_engine *e, const float *queries_dev, const QSlice *slices_dev,
                                const TileItem *items_dev, uint32_t item_begin, uint32_t n_items,
                                const uint32_t *item_q_dev, uint64_t *cand_dev, uint32_t *cand_cnt_dev,
-                               uint32_t *flags_dev);
+                               uint32_t *gthr_dev, uint32_t *flags_dev);
+cudaError_t launch_fill_u32(hvs_engine *e, uint32_t *dst, uint32_t value, size_t n);
 cudaError_t launch_finalize(hvs_engine *e, const float *queries_dev, const QSlice *slices_dev,
                             const uint32_t *tile_q_dev, uint32_t n_tile_q, const uint32_t *qoff_dev,
                             const uint32_t *qlists_dev, const uint64_t *cand_dev, const uint32_t *cand_cnt_dev,

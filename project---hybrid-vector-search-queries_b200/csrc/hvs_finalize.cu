@@ -50,16 +50,16 @@ k_finalize(const float *__restrict__ queries, const QSlice *__restrict__ slices,
     for (uint32_t li = l0; li < l1; ++li) {
         const uint32_t list = qlists[li];
         const uint32_t c = min(cand_cnt[list], (uint32_t)KOUT);
-        if ((uint32_t)tid < c) {
-            const uint64_t k = cand[(size_t)list * KOUT + tid];
+        for (uint32_t e = tid; e < c; e += FT) {
+            const uint64_t k = cand[(size_t)list * KOUT + e];
             const float s = okey_inv((uint32_t)(k >> 32));
             if (s < S.p1.thr) {
                 const uint32_t slot = atomicAdd(&S.p1.cnt, 1u);
-                S.p1.cand[slot] = k;                         // cnt <= P1CAP - FT before every list
+                S.p1.cand[slot] = k;                         // cnt <= P1CAP - KOUT before every list
             }
         }
         __syncthreads();
-        if (S.p1.cnt > (uint32_t)(P1CAP - FT)) S.p1.compact(tid, FT, margin, P1KEEP);
+        if (S.p1.cnt > (uint32_t)(P1CAP - KOUT)) S.p1.compact(tid, FT, margin, P1KEEP);
     }
     S.p1.compact(tid, FT, margin, P1KEEP);
     if (S.p1.overflow && tid == 0) flags[q] = 1u;            // K4 re-solves this query
@@ -183,6 +183,19 @@ cudaError_t launch_rescore(hvs_engine *e, const float *queries_dev, uint32_t m, 
     k_rescore<<<(unsigned)((total + 127) / 128), 128, 0, e->stream>>>(queries_dev, m, ids_dev, ix.inv_t.as<uint32_t>(),
                                                                         ix.x[ARENA_T].as<float>(), ix.tail.as<float>(),
                                                                         ix.n_total, ix.id_offset, out_dev);
+    return cudaGetLastError();
+}
+
+__global__ void k_fill_u32(uint32_t *__restrict__ dst, uint32_t value, size_t n)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = value;
+}
+
+cudaError_t launch_fill_u32(hvs_engine *e, uint32_t *dst, uint32_t value, size_t n)
+{
+    if (!n) return cudaSuccess;
+    k_fill_u32<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(dst, value, n);
     return cudaGetLastError();
 }
 

@@ -19,12 +19,15 @@ __host__ __device__ inline float margin_ffma(float qnorm, float xnorm_max)
     float eps = 2.0f * 104.0f * 5.9604645e-8f * r * r;
     return 2.0f * eps * 1.5f + 1e-30f;
 }
-// BF16 operands (round-to-nearest, relative 2^-9 each) in the tcgen05 pass (K3); the split
-// ||x||^2 and fp32 accumulation add only fp32-level terms (covered by the margin_ffma part).
+// BF16 operands in the tcgen05 pass (K3).  bf16 keeps 8 significant bits, round-to-nearest: unit
+// roundoff 2^-8 per operand, so each product q_i x_i is off by at most (2^-7 + 2^-16)|q_i x_i| and
+// |sum - q.x| <= (2^-7 + 2^-16) ||q|| ||x|| (Cauchy-Schwarz); the score carries -2 q.x.  The split
+// ||x||^2 (three bf16 terms) and the tensor core's fp32 accumulation add only fp32-level terms,
+// covered generously by 4 x the K2 margin.
 __host__ __device__ inline float margin_tensor(float qnorm, float xnorm_max)
 {
-    float eps = 2.0f * (2.0f / 512.0f + 1.0f / 262144.0f) * sqrtf(qnorm) * sqrtf(xnorm_max);
-    return 2.0f * eps * 1.05f + margin_ffma(qnorm, xnorm_max) * 4.0f;
+    float eps = 2.0f * (1.0f / 128.0f + 1.0f / 65536.0f) * sqrtf(qnorm) * sqrtf(xnorm_max);
+    return 2.0f * eps * 1.02f + margin_ffma(qnorm, xnorm_max) * 4.0f;
 }
 
 }  // namespace hvs

@@ -84,13 +84,22 @@ cudaError_t launch_plan_search(hvs_engine *e, const float *queries_dev, uint32_t
 // ------------------------------------------------------------------------------------------------
 // Host planner.
 //
-// A tile item makes <= 128 queries sweep a run of arena rows together, so its cost is
-// rows x 128 pair-slots whatever the queries need; a direct scan costs exactly the rows the query
-// needs but runs at HBM speed (400 B per pair).  A query goes to the tile path when, averaged over
-// its slice, at least 128 / direct_cost_ratio other queries want the same rows.
+// A tile item makes a batch of queries sweep a run of arena rows together.  On the FFMA kernel its
+// cost is rows x 128 pair-slots whatever the queries need, while a direct scan costs exactly the rows
+// the query needs but runs at HBM speed (400 B per pair): a query takes the FFMA tile path when,
+// averaged over its slice, at least 128 / direct_cost_ratio other queries want the same rows.  On the
+// tensor kernel pair-slots are nearly free and the sweep is priced by the bytes of the bf16 image it
+// streams (224 B per row per <= 256 queries), so sharing the rows with about one other query is enough.
+// One solve never mixes the two tile kernels: their candidate thresholds are shared per query and
+// carry different error margins.
+//
+// Everything is counting sorts over (chunk, query) incidences -- O(m log m + incidences), no
+// comparator sorts over the incidence list.
 void plan_build(const QSlice *sl, uint32_t m, const PlanParams &pp, Plan &P)
 {
     P = Plan();
+    const bool tensor = pp.tensor_available && (pp.mode == HVS_MODE_AUTO || pp.mode == HVS_MODE_TENSOR);
+    const uint32_t BQ = tensor ? (uint32_t)QT_TENSOR : (uint32_t)QT;
     std::vector<uint8_t> is_tile(m, 0);
     uint64_t tile_qrows = 0;
     for (uint32_t i = 0; i < m; ++i) {
@@ -99,6 +108,7 @@ void plan_build(const QSlice *sl, uint32_t m, const PlanParams &pp, Plan &P)
     }
     if (pp.mode != HVS_MODE_DIRECT) {
         constexpr uint32_t CELL = 1024;
+        const double need = tensor ? pp.tensor_min_depth : (double)QT / pp.direct_cost_ratio;
         for (uint32_t a = 0; a < 2; ++a) {
             uint32_t maxend = 0;
             for (uint32_t i = 0; i < m; ++i)
@@ -114,9 +124,8 @@ void plan_build(const QSlice *sl, uint32_t m, const PlanParams &pp, Plan &P)
             std::vector<int64_t> pref(ncell + 1, 0);   // pref[c] = sum of depth over cells < c
             int64_t run = 0;
             for (uint32_t c = 0; c < ncell; ++c) { run += depth[c]; pref[c + 1] = pref[c] + run; }
-            const double need = (double)QT / pp.direct_cost_ratio;
             for (uint32_t i = 0; i < m; ++i)
-                if (sl[i].arena == a && sl[i].end > sl[i].begin) {
+                if (sl[i].arena == a && sl[i].end - sl[i].begin >= pp.min_tile_len) {
                     uint32_t c0 = sl[i].begin / CELL, c1 = (sl[i].end - 1) / CELL + 1;
                     double avg = (double)(pref[c1] - pref[c0]) / (double)(c1 - c0);
                     if (avg >= need) {
@@ -138,79 +147,84 @@ void plan_build(const QSlice *sl, uint32_t m, const PlanParams &pp, Plan &P)
     if (!tile_qrows) return;
 
     // chunk size: aim at ~16 items per SM over the whole job, power of two
-    uint64_t want = tile_qrows / ((uint64_t)QT * 16 * 148);
+    uint64_t want = tile_qrows / ((uint64_t)BQ * 16 * 148);
     uint32_t R = 8192;
     while ((uint64_t)R * 2 <= want && R < pp.chunk_rows * 4u) R *= 2;
     if (R > (1u << 19)) R = 1u << 19;
 
-    struct Inc { uint32_t chunk, q; };
+    std::vector<uint32_t> order, cstart, fill;
     for (uint32_t a = 0; a < 2; ++a) {
-        std::vector<Inc> inc;
+        // tile queries of this arena ordered by (begin, end, index): each chunk's batches then group
+        // queries with similar slices, which keeps the union of rows an item sweeps tight
+        order.clear();
+        uint32_t maxend = 0;
         for (uint32_t i = 0; i < m; ++i)
-            if (is_tile[i] && sl[i].arena == a)
-                for (uint32_t c = sl[i].begin / R; c <= (sl[i].end - 1) / R; ++c) inc.push_back({c, i});
-        if (inc.empty()) continue;
-        std::sort(inc.begin(), inc.end(), [&](const Inc &x, const Inc &y) {
-            if (x.chunk != y.chunk) return x.chunk < y.chunk;
-            if (sl[x.q].begin != sl[y.q].begin) return sl[x.q].begin < sl[y.q].begin;
-            if (sl[x.q].end != sl[y.q].end) return sl[x.q].end < sl[y.q].end;
-            return x.q < y.q;
+            if (is_tile[i] && sl[i].arena == a) { order.push_back(i); maxend = std::max(maxend, sl[i].end); }
+        if (order.empty()) continue;
+        std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
+            if (sl[x].begin != sl[y].begin) return sl[x].begin < sl[y].begin;
+            if (sl[x].end != sl[y].end) return sl[x].end < sl[y].end;
+            return x < y;
         });
-        size_t p = 0;
-        while (p < inc.size()) {
-            size_t e = p;
-            while (e < inc.size() && inc[e].chunk == inc[p].chunk) ++e;
-            const uint32_t c0 = inc[p].chunk * R;
+        const uint32_t nchunk = (maxend + R - 1) / R;
+        cstart.assign(nchunk + 1, 0);
+        for (uint32_t i : order)
+            for (uint32_t c = sl[i].begin / R; c <= (sl[i].end - 1) / R; ++c) ++cstart[c + 1];
+        for (uint32_t c = 0; c < nchunk; ++c) cstart[c + 1] += cstart[c];
+        fill.assign(cstart[nchunk], 0);
+        {
+            std::vector<uint32_t> cur(cstart.begin(), cstart.end() - 1);
+            for (uint32_t i : order)
+                for (uint32_t c = sl[i].begin / R; c <= (sl[i].end - 1) / R; ++c) fill[cur[c]++] = i;
+        }
+        for (uint32_t c = 0; c < nchunk; ++c) {
+            const uint32_t c0 = c * R;
             const uint64_t c1 = (uint64_t)c0 + R;
-            for (size_t t = p; t < e; t += QT) {
-                size_t te = std::min(e, t + (size_t)QT);
+            for (uint32_t t = cstart[c]; t < cstart[c + 1]; t += BQ) {
+                const uint32_t te = std::min(cstart[c + 1], t + BQ);
                 TileItem it{};
                 it.arena = a;
                 uint32_t lo = 0xffffffffu, hi = 0;
-                for (size_t k = t; k < te; ++k) {
-                    lo = std::min(lo, std::max(sl[inc[k].q].begin, c0));
-                    hi = std::max(hi, (uint32_t)std::min<uint64_t>(sl[inc[k].q].end, c1));
+                for (uint32_t k = t; k < te; ++k) {
+                    lo = std::min(lo, std::max(sl[fill[k]].begin, c0));
+                    hi = std::max(hi, (uint32_t)std::min<uint64_t>(sl[fill[k]].end, c1));
                 }
                 it.row_begin = lo; it.row_end = hi;
-                it.nq = (uint32_t)(te - t);
+                it.nq = te - t;
                 it.q_off = (uint32_t)P.item_q.size();
-                for (size_t k = t; k < te; ++k) P.item_q.push_back(inc[k].q);
-                uint32_t rows = hi - lo;
-                bool tensor = false;
-                if (pp.tensor_available) {
-                    if (pp.mode == HVS_MODE_TENSOR) tensor = true;
-                    else if (pp.mode == HVS_MODE_AUTO) tensor = rows >= pp.tensor_min_rows && it.nq >= pp.tensor_min_q;
-                }
+                P.item_q.insert(P.item_q.end(), fill.begin() + t, fill.begin() + te);
                 it.kind = tensor ? 1u : 0u;
                 P.items.push_back(it);
-                P.pairs_computed += (uint64_t)rows * it.nq;
+                P.pairs_computed += (uint64_t)(hi - lo) * it.nq;
             }
-            p = e;
         }
     }
-    // longest first (LPT) within each kernel kind; equal-cost items stay in (arena,row) order so
-    // CTAs running concurrently share the same X chunk in L2
+    // longest first (LPT); equal-cost items stay in (arena,row) order so that CTAs running
+    // concurrently share the same rows in L2
     std::stable_sort(P.items.begin(), P.items.end(), [](const TileItem &x, const TileItem &y) {
-        if (x.kind != y.kind) return x.kind < y.kind;
         return (x.row_end - x.row_begin) > (y.row_end - y.row_begin);
     });
-    // candidate lists: item-major after sorting
-    std::vector<std::vector<uint32_t>> lists_of(m);
+    // candidate lists: item-major after sorting; CSR per tile query by counting
+    std::vector<uint32_t> nlist(m, 0);
     uint32_t off = 0;
     for (auto &it : P.items) {
         it.out_off = off;
-        for (uint32_t s = 0; s < it.nq; ++s) lists_of[P.item_q[it.q_off + s]].push_back(off + s);
+        for (uint32_t s = 0; s < it.nq; ++s) ++nlist[P.item_q[it.q_off + s]];
         off += it.nq;
         if (it.kind) ++P.n_tensor; else ++P.n_ffma;
     }
     P.n_lists = off;
+    std::vector<uint32_t> qpos(m, 0);
     P.q_list_off.push_back(0);
     for (uint32_t i = 0; i < m; ++i)
         if (is_tile[i]) {
+            qpos[i] = P.q_list_off.back();
             P.tile_q.push_back(i);
-            for (uint32_t l : lists_of[i]) P.q_lists.push_back(l);
-            P.q_list_off.push_back((uint32_t)P.q_lists.size());
+            P.q_list_off.push_back(qpos[i] + nlist[i]);
         }
+    P.q_lists.resize(P.q_list_off.back());
+    for (const auto &it : P.items)
+        for (uint32_t s = 0; s < it.nq; ++s) P.q_lists[qpos[P.item_q[it.q_off + s]]++] = it.out_off + s;
 }
 
 }  // namespace hvs

@@ -12,7 +12,7 @@
 //
 // Scores are s = ||x||^2 - 2 q.x (the query-constant ||q||^2 is dropped).  A score survives when it
 // is below the query's running threshold  s_(100) + margin ; survivors go to a 32-slot shared-memory
-// buffer per query and are merged by one warp into the query's sorted candidate list (<= 128 entries,
+// buffer per query and are merged by one warp into the query's sorted candidate list (<= 256 entries,
 // L2-resident) when the buffer fills.  `margin` bounds the rounding difference between this kernel's
 // arithmetic and the reference's (hvs_margin.cuh), so the list provably contains the reference's
 // top-100; K5 (hvs_finalize.cu) re-ranks it with the reference's own arithmetic.
@@ -38,7 +38,6 @@ struct TileSmem {
     alignas(16) float xn[2][TR];         // ||x||^2 of the tile rows
     alignas(16) float q[TQ * DIM];       // the item's query vectors, [query][dim]
     uint64_t buf[TQ][CB];                // survivors waiting to be merged
-    uint64_t scratch[NWARP][256];        // per-warp merge area
     float thr[TQ];                       // accept when s < thr
     float margin[TQ];
     uint32_t bcnt[TQ];                   // entries pushed to buf (may exceed CB: the excess is retried)
@@ -52,44 +51,34 @@ struct TileSmem {
 
 // Merge the survivor buffer of query slot `qq` into its sorted candidate list.  One warp.
 __device__ __forceinline__ void merge_slot(TileSmem &S, const TileItem &it, int qq, uint64_t *__restrict__ cand,
-                                           uint32_t *__restrict__ flags, int warp, int lane)
+                                           uint32_t *__restrict__ gthr, uint32_t *__restrict__ flags, int lane)
 {
     const uint32_t nb = min(S.bcnt[qq], (uint32_t)CB);
     const uint32_t nl = S.lcnt[qq];
     uint64_t *L = cand + (size_t)(it.out_off + qq) * KOUT;
-    uint64_t *sc = S.scratch[warp];
-    const uint32_t total = nl + nb;
-    const int n = next_pow2(total < 2 ? 2 : (int)total);
-    for (int e = lane; e < n; e += 32)
-        sc[e] = (uint32_t)e < nl ? L[e] : ((uint32_t)e < total ? S.buf[qq][e - nl] : KEY_INF);
-    __syncwarp();
-    warp_bitonic_sort(sc, n, lane);
-    uint32_t keep = total;
-    if (total >= (uint32_t)K) {
-        const float sk = okey_inv((uint32_t)(sc[K - 1] >> 32));
-        const float lim = sk + S.margin[qq];
-        uint32_t last = K;
-        for (uint32_t e = K + lane; e < total; e += 32)
-            if (okey_inv((uint32_t)(sc[e] >> 32)) <= lim) last = e + 1;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
-        keep = last;
-        if (keep > (uint32_t)KOUT) {       // more rows inside the margin than the list can hold:
-            keep = KOUT;                   // the guarantee is gone, K4 re-solves this query exactly
-            if (lane == 0) flags[S.qid[qq]] = 1u;
-        }
-        if (lane == 0) S.thr[qq] = nextafterf(lim, __int_as_float(0x7f800000));
+    const uint64_t nk = (uint32_t)lane < nb ? S.buf[qq][lane] : KEY_INF;
+    float lim;
+    bool ovf;
+    const uint32_t keep = warp_merge_list<KOUT>(L, nl, nk, nb, S.margin[qq], lim, ovf, lane);
+    if (lane == 0) {
+        S.lcnt[qq] = keep;
+        S.bcnt[qq] = 0;
+        const uint32_t qid = S.qid[qq];
+        if (ovf) flags[qid] = 1u;          // more rows inside the margin than the list holds: K4 re-solves exactly
+        // thresholds are shared by every CTA that works on this query (other row chunks)
+        const float mine = nextafterf(lim, __int_as_float(0x7f800000));
+        const float theirs = okey_inv(ld_relaxed_u32(&gthr[qid]));
+        if (mine < theirs) atomicMin(&gthr[qid], okey(mine));
+        S.thr[qq] = fminf(S.thr[qq], fminf(mine, theirs));
     }
-    for (uint32_t e = lane; e < keep; e += 32) L[e] = sc[e];
-    if (lane == 0) { S.lcnt[qq] = keep; S.bcnt[qq] = 0; }
     __syncwarp();
 }
 
 __device__ __forceinline__ void merge_pass(TileSmem &S, const TileItem &it, uint32_t min_fill, uint64_t *__restrict__ cand,
-                                           uint32_t *__restrict__ flags, int warp, int lane)
+                                           uint32_t *__restrict__ gthr, uint32_t *__restrict__ flags, int warp, int lane)
 {
     for (int qq = warp; qq < (int)it.nq; qq += NWARP)
-        if (S.bcnt[qq] >= min_fill) merge_slot(S, it, qq, cand, flags, warp, lane);
+        if (S.bcnt[qq] >= min_fill) merge_slot(S, it, qq, cand, gthr, flags, lane);
 }
 
 }  // namespace
@@ -97,7 +86,8 @@ __device__ __forceinline__ void merge_pass(TileSmem &S, const TileItem &it, uint
 __global__ void __launch_bounds__(NT, 1)
 k_tile_ffma(const float *__restrict__ queries, const QSlice *__restrict__ slices, const TileItem *__restrict__ items,
             const uint32_t *__restrict__ item_q, Arena a0, Arena a1, uint32_t n_rows, float xnorm_max, float margin_scale,
-            uint64_t *__restrict__ cand, uint32_t *__restrict__ cand_cnt, uint32_t *__restrict__ flags)
+            uint64_t *__restrict__ cand, uint32_t *__restrict__ cand_cnt, uint32_t *__restrict__ gthr,
+            uint32_t *__restrict__ flags)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TileSmem &S = *reinterpret_cast<TileSmem *>(smem_raw);
@@ -117,19 +107,19 @@ k_tile_ffma(const float *__restrict__ queries, const QSlice *__restrict__ slices
     __syncthreads();
     if (tid < TQ) {
         uint32_t lo = 1, hi = 0, id = 0xffffffffu;
-        float mg = 0.f;
+        float mg = 0.f, th = __int_as_float(0xff800000);   // unused query slots never accept a row (nobody merges their buffers)
         if ((uint32_t)tid < it.nq) {
             id = item_q[it.q_off + tid];
             const QSlice sl = slices[id];
             lo = max(sl.begin, it.row_begin);
             hi = min(sl.end, it.row_end);
             mg = margin_ffma(sl.qnorm, xnorm_max) * margin_scale;
+            th = okey_inv(ld_relaxed_u32(&gthr[id]));   // what other CTAs already know about this query
             atomicMax(&S.lo_max, lo);
             atomicMin(&S.hi_min, hi);
         }
         S.qid[tid] = id; S.qlo[tid] = lo; S.qhi[tid] = hi; S.margin[tid] = mg;
-        // unused query slots of a short item must never accept a row (nobody merges their buffers)
-        S.thr[tid] = __int_as_float((uint32_t)tid < it.nq ? 0x7f800000 : 0xff800000);
+        S.thr[tid] = th;
         S.bcnt[tid] = 0; S.lcnt[tid] = 0;
     }
     for (int idx = tid; idx < TQ * (DIM / 4); idx += NT) {
@@ -228,7 +218,7 @@ k_tile_ffma(const float *__restrict__ queries, const QSlice *__restrict__ slices
         if (S.need[t % 3]) {                               // uniform: read after the barrier
             uint32_t min_fill = CB / 2;
             for (;;) {
-                merge_pass(S, it, min_fill, cand, flags, warp, lane);
+                merge_pass(S, it, min_fill, cand, gthr, flags, warp, lane);
                 __syncthreads();
                 if (pend) {                                // retry the pushes that found the buffer full
 #pragma unroll
@@ -255,14 +245,14 @@ k_tile_ffma(const float *__restrict__ queries, const QSlice *__restrict__ slices
         }
     }
     __syncthreads();
-    merge_pass(S, it, 1u, cand, flags, warp, lane);
+    merge_pass(S, it, 1u, cand, gthr, flags, warp, lane);
     __syncthreads();
     if ((uint32_t)tid < it.nq) cand_cnt[it.out_off + tid] = S.lcnt[tid];
 }
 
 cudaError_t launch_tile_ffma(hvs_engine *e, const float *queries_dev, const QSlice *slices_dev, const TileItem *items_dev,
                              uint32_t item_begin, uint32_t n_items, const uint32_t *item_q_dev, uint64_t *cand_dev,
-                             uint32_t *cand_cnt_dev, uint32_t *flags_dev, float margin_scale)
+                             uint32_t *cand_cnt_dev, uint32_t *gthr_dev, uint32_t *flags_dev, float margin_scale)
 {
     if (!n_items) return cudaSuccess;
     static bool attr_done = false;
@@ -275,7 +265,7 @@ cudaError_t launch_tile_ffma(hvs_engine *e, const float *queries_dev, const QSli
     const Index &ix = e->index;
     k_tile_ffma<<<n_items, NT, smem, e->stream>>>(queries_dev, slices_dev, items_dev + item_begin, item_q_dev, ix.arena(0),
                                                    ix.arena(1), ix.n, ix.xnorm_max, margin_scale, cand_dev, cand_cnt_dev,
-                                                   flags_dev);
+                                                   gthr_dev, flags_dev);
     return cudaGetLastError();
 }
 

@@ -62,6 +62,92 @@ __device__ __forceinline__ float okey_inv(uint32_t k)
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
+// Warp-cooperative merge of up to 32 new keys (lane i passes key i, KEY_INF when it has none) into a
+// sorted candidate list L[0..nl) in global memory (nl <= KOUT_), in place and without scratch:
+// the new keys are sorted across lanes with shuffles, every element's merged position is its own
+// index plus the number of elements of the other sequence that precede it, and everything is read
+// into registers before anything is written.  Keeps the entries whose score is within `margin` of
+// the K-th best (all of them while fewer than K are known).  Returns the new length; lim_out is
+// (K-th score + margin) or +inf; overflow is set when more than KOUT_ entries sit inside the margin.
+// Keys must be distinct (they carry the row index).
+template <int KOUT_>
+__device__ __forceinline__ uint32_t warp_merge_list(uint64_t *__restrict__ L, uint32_t nl, uint64_t newkey, uint32_t nb,
+                                                    float margin, float &lim_out, bool &overflow, int lane)
+{
+    constexpr int PER = KOUT_ / 32;
+    constexpr uint32_t FULLMASK = 0xffffffffu;
+    uint64_t key = newkey;
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1)
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const uint64_t other = __shfl_xor_sync(FULLMASK, key, j);
+            const bool take_min = ((lane & j) == 0) == ((lane & k) == 0);
+            key = take_min ? (key < other ? key : other) : (key < other ? other : key);
+        }
+    uint64_t lk[PER];
+    uint32_t cl[PER];
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+        const uint32_t i = lane + 32 * j;
+        lk[j] = i < nl ? L[i] : KEY_INF;
+        cl[j] = 0;
+    }
+    uint32_t myrank = 0;
+    for (uint32_t t = 0; t < nb; ++t) {
+        const uint64_t nk = __shfl_sync(FULLMASK, key, t);
+        uint32_t c = 0;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            const bool lt = lk[j] < nk;
+            c += lt;
+            cl[j] += !lt;
+        }
+        c = __reduce_add_sync(FULLMASK, c);
+        if ((uint32_t)lane == t) myrank = c;
+    }
+    const uint32_t total = nl + nb;
+    uint32_t keep = total;
+    lim_out = __int_as_float(0x7f800000);
+    overflow = false;
+    if (total >= (uint32_t)K) {
+        uint32_t hi = 0;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            const uint32_t i = lane + 32 * j;
+            if (i < nl && i + cl[j] == (uint32_t)(K - 1)) hi = (uint32_t)(lk[j] >> 32);
+        }
+        if ((uint32_t)lane < nb && lane + myrank == (uint32_t)(K - 1)) hi = (uint32_t)(key >> 32);
+        hi = __reduce_max_sync(FULLMASK, hi);
+        const float lim = okey_inv(hi) + margin;
+        uint32_t nin = 0;
+#pragma unroll
+        for (int j = 0; j < PER; ++j)
+            if ((uint32_t)(lane + 32 * j) < nl && okey_inv((uint32_t)(lk[j] >> 32)) <= lim) ++nin;
+        if ((uint32_t)lane < nb && okey_inv((uint32_t)(key >> 32)) <= lim) ++nin;
+        nin = __reduce_add_sync(FULLMASK, nin);
+        keep = nin;
+        if (keep > (uint32_t)KOUT_) { keep = KOUT_; overflow = true; }
+        lim_out = lim;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+        const uint32_t i = lane + 32 * j, pos = i + cl[j];
+        if (i < nl && pos < keep) L[pos] = lk[j];
+    }
+    if ((uint32_t)lane < nb && lane + myrank < keep) L[lane + myrank] = key;
+    __syncwarp();
+    return keep;
+}
+
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 __device__ __forceinline__ int next_pow2(int v)
 {
     int p = 1;

@@ -36,13 +36,20 @@ def run(n, m, ncat, modes, types=(0, 1, 2, 3), check_n=0, reps=2):
             print(f"   oracle check {a}: {p.summary()}")
 
 if __name__ == "__main__":
-    with hvs.Engine() as e:
-        for _ in range(2):
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    ALL = {"direct": hvs.MODE_DIRECT, "exact": hvs.MODE_EXACT, "auto": hvs.MODE_AUTO}
+    names = sys.argv[2].split(",") if len(sys.argv) > 2 else ["direct", "exact", "auto"]
+    M = [(k, ALL[k]) for k in names]
+    FAST = [(k, ALL[k]) for k in names if k != "direct"]
+    if which in ("all", "peak"):
+        with hvs.Engine() as e:
             print("ffma peak TF/s, MHz:", e.measure_ffma_peak(5), flush=True)
-    M = [("direct", hvs.MODE_DIRECT), ("exact", hvs.MODE_EXACT)]
-    run(10_000, 100, 10, M, check_n=100)
-    run(200_000, 1024, 10, M, check_n=32)
-    run(1_000_000, 4096, 100, M, check_n=16)
-    run(1_000_000, 10_000, 100, [("exact", hvs.MODE_EXACT)], check_n=8)
-    run(4_000_000, 8192, 100, [("exact", hvs.MODE_EXACT)], types=(0,), check_n=4)
-    run(10_000_000, 40_000, 100, [("exact", hvs.MODE_EXACT)], check_n=0, reps=1)
+    if which in ("all", "small"):
+        run(10_000, 100, 10, M, check_n=100)
+        run(200_000, 1024, 10, M, check_n=32)
+    if which in ("all", "mid"):
+        run(1_000_000, 4096, 100, M, check_n=16)
+        run(2_000_000, 2048, 10, FAST, types=(0,), check_n=4)
+    if which in ("all", "big"):
+        run(10_000_000, 40_000, 100, FAST, check_n=8, reps=2)
+        run(10_000_000, 40_000, 100, FAST, types=(0,), check_n=4, reps=2)
