@@ -53,12 +53,13 @@ struct Index {
     DevBuf x[2];               // [n][100] fp32
     DevBuf ids[2];             // [n] u32
     DevBuf xnorm[2];           // [n] f32
-    DevBuf xb[2];              // bf16 tile image for the tensor path: [n_pad][128] bf16 (cols 100..102 = split ||x||^2)
+    DevBuf xb[2];              // fp16 image for the tensor path, canonical K-major core-matrix layout, 224 B per row
     DevBuf keys_t;             // [n] u32  sorted ord(T)
     DevBuf keys_ct;            // [n] u64  sorted ord(C)<<32 | ord(T)
     DevBuf tail;               // [100][100] fp32: tail[s-1] = vector of row n_total - s  (pad rule)
     DevBuf inv_t;              // [n_total] u32: original row -> arena-T row (0xFFFFFFFF if not indexed); rescore only
     float xnorm_max = 0.f;     // max ||x||^2 over indexed rows (margin bound)
+    float img_scale = 1.f;     // sx: power of two applied to x before the fp16 image is written (K3)
     bool built = false;
     Arena arena(int a) const
     {
@@ -73,6 +74,7 @@ struct Index {
 constexpr int QT = 128;          // queries per FFMA tile item (K2)
 constexpr int QT_TENSOR = 256;   // queries per tensor tile item (K3): two M=128 halves share every data stage
 constexpr int KOUT = 256;        // candidates an item hands to finalize per query (<= this many)
+constexpr int TENSOR_POOL = 512; // K3: survivor pool entries per (CTA, query) in global memory
 
 struct TileItem {              // one CTA-sized unit of work: <= 128 queries sweep arena rows [row_begin,row_end)
     uint32_t arena;
@@ -122,7 +124,7 @@ struct hvs_engine {
     hvs_stats stats{};
     // per-solve scratch (grow-only)
     hvs::DevBuf d_queries, d_out, d_slices, d_direct_q, d_items, d_item_q, d_tile_q, d_qoff, d_qlists;
-    hvs::DevBuf d_cand, d_cand_cnt, d_scratch, d_flags, d_gthr, d_work_counter, d_rescore_ids, d_rescore_out;
+    hvs::DevBuf d_cand, d_cand_cnt, d_scratch, d_flags, d_gthr, d_pool, d_work_counter, d_rescore_ids, d_rescore_out;
     hvs::HostPinned h_slices, h_stage;
     cudaEvent_t ev[12]{};
     hvs::Plan plan;

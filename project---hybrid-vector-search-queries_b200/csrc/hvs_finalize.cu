@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(FT)
 k_finalize(const float *__restrict__ queries, const QSlice *__restrict__ slices, const uint32_t *__restrict__ tile_q,
            const uint32_t *__restrict__ qoff, const uint32_t *__restrict__ qlists, const uint64_t *__restrict__ cand,
            const uint32_t *__restrict__ cand_cnt, uint32_t *__restrict__ flags, Arena a0, Arena a1,
-           const float *__restrict__ tail, uint32_t n_total, float xnorm_max, int tensor_lists, int partial,
+           const float *__restrict__ tail, uint32_t n_total, float xnorm_max, float tensor_sx, int partial,
            uint32_t *__restrict__ out_ids, float *__restrict__ out_dist, uint32_t *__restrict__ out_count)
 {
     __shared__ FinSmem S;
@@ -42,8 +42,9 @@ k_finalize(const float *__restrict__ queries, const QSlice *__restrict__ slices,
     if (tid < DIM / 4)
         reinterpret_cast<float4 *>(S.q)[tid] = reinterpret_cast<const float4 *>(queries + (size_t)q * QROW + 4)[tid];
     __syncthreads();
-    // lists written by K3 carry bf16-level error, lists written by K2 fp32-level error
-    const float margin = tensor_lists ? margin_tensor(sl.qnorm, xnorm_max) : margin_ffma(sl.qnorm, xnorm_max);
+    // lists written by K3 hold fp16-level scores in units of sx^2 d; lists written by K2 fp32-level scores in units of d
+    const float margin = tensor_sx > 0.f ? margin_tensor(sl.qnorm, xnorm_max, tensor_sx) * tensor_sx * tensor_sx
+                                         : margin_ffma(sl.qnorm, xnorm_max);
 
     // phase 1: the rows whose approximate score is within the margin of the global 100-th best
     const uint32_t l0 = qoff[blockIdx.x], l1 = qoff[blockIdx.x + 1];
@@ -85,7 +86,7 @@ cudaError_t launch_finalize(hvs_engine *e, const float *queries_dev, const QSlic
     const Index &ix = e->index;
     k_finalize<<<n_tile_q, FT, 0, e->stream>>>(queries_dev, slices_dev, tile_q_dev, qoff_dev, qlists_dev, cand_dev, cand_cnt_dev,
                                                 flags_dev, ix.arena(0), ix.arena(1), ix.tail.as<float>(), ix.n_total,
-                                                ix.xnorm_max, e->plan.n_tensor ? 1 : 0, partial ? 1 : 0, out_ids,
+                                                ix.xnorm_max, e->plan.n_tensor ? ix.img_scale : 0.f, partial ? 1 : 0, out_ids,
                                                 out_dist, out_count);
     return cudaGetLastError();
 }

@@ -9,6 +9,8 @@
 // consecutive rows is ONE contiguous block that the TMA engine moves with a single 1-D bulk copy),
 // the original row ids, ||x||^2, and the sorted keys for binary search.  Never sees queries
 // (contest rule, README.md:68).  HBM-bound: ~2 sorts + 2 gathers of 400 B/row.
+#include <cmath>
+
 #include <cub/device/device_radix_sort.cuh>
 
 #include "hvs_engine.h"
@@ -76,7 +78,7 @@ __global__ void k_max_f32(const float *__restrict__ v, uint32_t n, uint32_t *__r
     if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(m));   // non-negative floats order like their bits
 }
 
-void build_bf16_image(hvs_engine *e, int a);   // hvs_tile_tensor.cu
+void build_tensor_image(hvs_engine *e, int a);   // hvs_tile_tensor.cu
 
 #define CK(call)                                                                     \
     do {                                                                             \
@@ -163,11 +165,20 @@ cudaError_t index_build_device(hvs_engine *e, const float *rows, uint32_t n_tota
     }
     key_t_in.release(); key_ct_in.release(); perm_in.release(); perm_out.release(); tmp.release(); maxbits.release();
     if (rc != cudaSuccess) return rc;
-    if (tensor_path_available() && n) {
-        build_bf16_image(e, ARENA_T);
-        build_bf16_image(e, ARENA_CT);
+    ix.xb[0].release(); ix.xb[1].release();
+    ix.img_scale = 1.f;
+    if (tensor_path_available() && n && std::isfinite(ix.xnorm_max)) {
+        // sx = 2^e with sx^2 max||x||^2 <= 32000: every image element and every split-norm term fits fp16
+        if (ix.xnorm_max > 0.f) {
+            int ex = (int)std::floor(0.5 * std::log2(32000.0 / (double)ix.xnorm_max));
+            if (ex > 40) ex = 40;
+            if (ex < -40) ex = -40;
+            ix.img_scale = std::ldexp(1.0f, ex);
+        }
+        build_tensor_image(e, ARENA_T);
+        build_tensor_image(e, ARENA_CT);
         cudaError_t c = cudaStreamSynchronize(st);
-        if (c != cudaSuccess) { e->err = std::string("bf16 image: ") + cudaGetErrorString(c); return c; }
+        if (c != cudaSuccess) { e->err = std::string("fp16 image: ") + cudaGetErrorString(c); return c; }
     }
     ix.built = true;
     return cudaSuccess;

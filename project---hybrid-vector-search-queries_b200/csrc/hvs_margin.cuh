@@ -19,14 +19,17 @@ __host__ __device__ inline float margin_ffma(float qnorm, float xnorm_max)
     float eps = 2.0f * 104.0f * 5.9604645e-8f * r * r;
     return 2.0f * eps * 1.5f + 1e-30f;
 }
-// BF16 operands in the tcgen05 pass (K3).  bf16 keeps 8 significant bits, round-to-nearest: unit
-// roundoff 2^-8 per operand, so each product q_i x_i is off by at most (2^-7 + 2^-16)|q_i x_i| and
-// |sum - q.x| <= (2^-7 + 2^-16) ||q|| ||x|| (Cauchy-Schwarz); the score carries -2 q.x.  The split
-// ||x||^2 (three bf16 terms) and the tensor core's fp32 accumulation add only fp32-level terms,
-// covered generously by 4 x the K2 margin.
-__host__ __device__ inline float margin_tensor(float qnorm, float xnorm_max)
+// FP16 operands in the tcgen05 pass (K3): a_k = fp16(-2 sx q_k), b_k = fp16(sx x_k), sx a power of two.
+// fp16 keeps 11 significant bits (unit roundoff 2^-11) and flushes to multiples of 2^-24 below 2^-14,
+// so |fl(v) - v| <= 2^-11 |v| + 2^-25.  Summed over the 100 products (Cauchy-Schwarz, ||.||_1 <= 10 ||.||_2)
+// and divided by sx^2 to come back to the units of d:
+//   |sum fl(a_k) fl(b_k) - a.b| / sx^2  <=  (2^-10 + 2^-22) 2 ||q|| ||x||  +  2^-25 * 10.1 (2||q|| + ||x||) / sx
+// The split ||x||^2 (three fp16 terms, exact to below fp32 ulp) and the tensor core's fp32 accumulation
+// add only fp32-level terms, covered generously by 4 x the K2 margin.  Result in the units of d.
+__host__ __device__ inline float margin_tensor(float qnorm, float xnorm_max, float sx)
 {
-    float eps = 2.0f * (1.0f / 128.0f + 1.0f / 65536.0f) * sqrtf(qnorm) * sqrtf(xnorm_max);
+    const float nq = sqrtf(qnorm), nx = sqrtf(xnorm_max);
+    float eps = (1.0f / 1024.0f + 1.0f / 4194304.0f) * 2.0f * nq * nx + 2.98023224e-8f * 10.1f * (2.0f * nq + nx) / sx;
     return 2.0f * eps * 1.02f + margin_ffma(qnorm, xnorm_max) * 4.0f;
 }
 
