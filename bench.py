@@ -194,7 +194,7 @@ def run_b200(args, rank, world, local_rank):
     stream = torch.cuda.current_stream()
     data_sharded = world > 1 and args.variant == "data"
     if data_sharded:
-        lo, hi = rank * n // world, (rank + 1) * n // world
+        lo, hi = importlib.import_module(PKG + ".sharding").data_shard(n, rank, world)
         eng = hvs.Engine(device=local_rank, mode=mode, stream=stream.cuda_stream, id_offset=lo)
         eng.index_build(d[lo:hi])
     else:
@@ -210,18 +210,14 @@ def run_b200(args, rank, world, local_rank):
         p_dist = torch.empty((m, 100), dtype=torch.float32, device="cuda")
         p_ids = torch.empty((m, 100), dtype=torch.int32, device="cuda")
         p_cnt = torch.empty((m,), dtype=torch.int32, device="cuda")
-        g_dist = torch.empty((world, m, 100), dtype=torch.float32, device="cuda")
-        g_ids = torch.empty((world, m, 100), dtype=torch.int32, device="cuda")
-        g_cnt = torch.empty((world, m), dtype=torch.int32, device="cuda")
+        sharding = importlib.import_module(PKG + ".sharding")
         tail = torch.from_numpy(np.ascontiguousarray(d[n - 100:])).cuda()
     torch.cuda.synchronize()
 
     def step_device():
         if data_sharded:
             eng.solve_partial_device(q_dev, p_dist, p_ids, p_cnt)
-            dist.all_gather_into_tensor(g_dist, p_dist)
-            dist.all_gather_into_tensor(g_ids, p_ids)
-            dist.all_gather_into_tensor(g_cnt, p_cnt)
+            g_dist, g_ids, g_cnt = sharding.gather_partials(p_dist, p_ids, p_cnt, world)
             eng.merge_partials_device(q_dev, world, g_dist, g_ids, g_cnt, tail, n, out_dev)
         else:
             eng.solve_device(q_dev, out_dev)

@@ -99,7 +99,7 @@ extern "C" void hvs_destroy(hvs_engine *e)
     for (int a = 0; a < 2; ++a) { ix.x[a].release(); ix.ids[a].release(); ix.xnorm[a].release(); ix.xb[a].release(); }
     ix.keys_t.release(); ix.keys_ct.release(); ix.tail.release(); ix.inv_t.release();
     DevBuf *bufs[] = {&e->d_queries, &e->d_out, &e->d_slices, &e->d_direct_q, &e->d_items, &e->d_item_q, &e->d_tile_q,
-                      &e->d_qoff, &e->d_qlists, &e->d_cand, &e->d_cand_cnt, &e->d_scratch, &e->d_flags, &e->d_gthr, &e->d_pool,
+                      &e->d_qoff, &e->d_qlists, &e->d_cand, &e->d_cand_cnt, &e->d_scratch, &e->d_flags, &e->d_gthr, &e->d_pool, &e->d_gbest, &e->d_glock,
                       &e->d_work_counter, &e->d_rescore_ids, &e->d_rescore_out};
     for (DevBuf *b : bufs) b->release();
     e->h_slices.release(); e->h_stage.release();

@@ -75,6 +75,7 @@ constexpr int QT = 128;          // queries per FFMA tile item (K2)
 constexpr int QT_TENSOR = 256;   // queries per tensor tile item (K3): two M=128 halves share every data stage
 constexpr int KOUT = 256;        // candidates an item hands to finalize per query (<= this many)
 constexpr int TENSOR_POOL = 512; // K3: survivor pool entries per (CTA, query) in global memory
+constexpr int TENSOR_GBEST = 128; // K3: per-query global list of the best scores seen by any CTA
 
 struct TileItem {              // one CTA-sized unit of work: <= 128 queries sweep arena rows [row_begin,row_end)
     uint32_t arena;
@@ -124,7 +125,7 @@ struct hvs_engine {
     hvs_stats stats{};
     // per-solve scratch (grow-only)
     hvs::DevBuf d_queries, d_out, d_slices, d_direct_q, d_items, d_item_q, d_tile_q, d_qoff, d_qlists;
-    hvs::DevBuf d_cand, d_cand_cnt, d_scratch, d_flags, d_gthr, d_pool, d_work_counter, d_rescore_ids, d_rescore_out;
+    hvs::DevBuf d_cand, d_cand_cnt, d_scratch, d_flags, d_gthr, d_pool, d_gbest, d_glock, d_work_counter, d_rescore_ids, d_rescore_out;
     hvs::HostPinned h_slices, h_stage;
     cudaEvent_t ev[12]{};
     hvs::Plan plan;

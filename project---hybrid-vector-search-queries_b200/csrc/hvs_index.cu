@@ -167,7 +167,7 @@ cudaError_t index_build_device(hvs_engine *e, const float *rows, uint32_t n_tota
     if (rc != cudaSuccess) return rc;
     ix.xb[0].release(); ix.xb[1].release();
     ix.img_scale = 1.f;
-    if (tensor_path_available() && n && std::isfinite(ix.xnorm_max)) {
+    if (tensor_path_available() && n && n < 0x80000000u && std::isfinite(ix.xnorm_max)) {
         // sx = 2^e with sx^2 max||x||^2 <= 32000: every image element and every split-norm term fits fp16
         if (ix.xnorm_max > 0.f) {
             int ex = (int)std::floor(0.5 * std::log2(32000.0 / (double)ix.xnorm_max));

@@ -28,6 +28,8 @@
 //
 // Roofline: tensor pipe -- 2 x 7 MMAs (M128 N128 K16) = 896 tensor cycles per 128-row stage per SM;
 // the B stream is 28,672 B per stage per SM, read mostly from L2 (CTAs of one wave share the rows).
+#include <cstdlib>
+
 #include <cuda_fp16.h>
 
 #include "hvs_engine.h"
@@ -50,6 +52,9 @@ constexpr int NTHR = 320;
 constexpr int POOL = TENSOR_POOL;     // survivor pool entries per query (global memory)
 constexpr int PER = POOL / 32;        // pool entries per lane when a warp sorts it
 constexpr uint32_t FULL = 0xffffffffu;
+constexpr int GB = TENSOR_GBEST;      // per-query list of the best scores seen by ANY CTA (global memory)
+constexpr uint32_t ROW_MASK = 0x7fffffffu, CONTRIB = 0x80000000u;   // top bit of a key's row word: "score already in gbest"
+constexpr uint32_t NOKEY = 0xffffffffu;
 
 static_assert(QT_TENSOR == 256, "two M=128 halves");
 static_assert(POOL == 512 && KOUT <= POOL - TN, "pool must take a whole stage after a compaction");
@@ -111,15 +116,79 @@ struct QState {
     uint32_t cnt, qlo, qhi, qid;
 };
 
+// Warp-cooperative: merge up to 32 scores (one per lane, NOKEY for none; distinct rows) into the query's
+// global best-score list under the query's lock.  Returns the key of the list's K-th entry afterwards.
+// This is what makes thresholds tight everywhere: the K-th best score over ALL rows any CTA has seen
+// for this query bounds the final K-th best, whichever chunk of the slice a CTA is sweeping.
+__device__ __noinline__ uint32_t contribute32(uint32_t *__restrict__ gbest_q, uint32_t *__restrict__ lock_q, uint32_t newkey, int lane)
+{
+    uint32_t key = newkey;
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1)
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const uint32_t other = __shfl_xor_sync(FULL, key, j);
+            const bool take_min = ((lane & j) == 0) == ((lane & k) == 0);
+            key = take_min ? min(key, other) : max(key, other);
+        }
+    const uint32_t nb = __popc(__ballot_sync(FULL, key != NOKEY));
+    if (lane == 0) {
+        while (atomicCAS(lock_q, 0u, 1u) != 0u) __nanosleep(64);
+        __threadfence();
+    }
+    __syncwarp();
+    uint32_t g[GB / 32], cl[GB / 32];
+#pragma unroll
+    for (int j = 0; j < GB / 32; ++j) { g[j] = ld_relaxed_u32(gbest_q + lane + 32 * j); cl[j] = 0; }
+    uint32_t myrank = 0;
+    for (uint32_t t = 0; t < nb; ++t) {
+        const uint32_t nk = __shfl_sync(FULL, key, t);
+        uint32_t c = 0;
+#pragma unroll
+        for (int j = 0; j < GB / 32; ++j) {
+            const bool le = g[j] <= nk;       // equal scores: the list entry goes first
+            c += le;
+            cl[j] += !le;
+        }
+        c = __reduce_add_sync(FULL, c);
+        if ((uint32_t)lane == t) myrank = c;
+    }
+    __syncwarp();
+    uint32_t kth = 0;
+#pragma unroll
+    for (int j = 0; j < GB / 32; ++j) {
+        const uint32_t pos = lane + 32 * j + cl[j];
+        if (pos < (uint32_t)GB) {
+            if (cl[j]) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(gbest_q + pos), "r"(g[j]) : "memory");
+            if (pos == (uint32_t)(K - 1)) kth = g[j];
+        }
+    }
+    if ((uint32_t)lane < nb) {
+        const uint32_t pos = lane + myrank;
+        if (pos < (uint32_t)GB) {
+            asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(gbest_q + pos), "r"(key) : "memory");
+            if (pos == (uint32_t)(K - 1)) kth = key;
+        }
+    }
+    kth = __reduce_max_sync(FULL, kth);
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) atomicExch(lock_q, 0u);
+    return kth;
+}
+
 // Warp-cooperative: sort lane `l`'s pool in registers (bitonic over 32 lanes x PER registers,
-// element e = j*32 + lane), keep what is within the margin of the K-th best, tighten thresholds.
+// element e = j*32 + lane), keep what is within the margin of the K-th best, hand the best scores that
+// are news to the query's global list, tighten thresholds.
 struct CompactOut { uint32_t cnt; float thr; };
 __device__ __noinline__ CompactOut compact_lane(int l, uint32_t my_cnt, float my_thr, float my_margin, uint32_t my_qid,
                                                 uint64_t *__restrict__ pool_warp, uint32_t *__restrict__ gthr,
+                                                uint32_t *__restrict__ gbest, uint32_t *__restrict__ glock,
                                                 uint32_t *__restrict__ flags, int lane)
 {
     const uint32_t n = __shfl_sync(FULL, my_cnt, l);
     const float margin = __shfl_sync(FULL, my_margin, l);
+    const uint32_t qid = __shfl_sync(FULL, my_qid, l);
     uint64_t *P = pool_warp + (size_t)l * POOL;
     uint64_t k[PER];
 #pragma unroll
@@ -170,6 +239,20 @@ __device__ __noinline__ CompactOut compact_lane(int l, uint32_t my_cnt, float my
         keep = __reduce_add_sync(FULL, nin);
         if (keep > (uint32_t)KOUT) { keep = KOUT; ovf = true; }   // more rows inside the margin than a list may hold
     }
+    // the best GB entries that are not in the global list yet and would enter it
+    uint32_t *gbest_q = gbest + (size_t)qid * GB;
+    uint32_t gk = ld_relaxed_u32(gbest_q + GB - 1);               // worst score the global list still holds
+    uint32_t kth = ld_relaxed_u32(gbest_q + K - 1);
+#pragma unroll
+    for (int j = 0; j < GB / 32; ++j) {
+        const uint32_t sc = (uint32_t)(k[j] >> 32);
+        const bool want = (uint32_t)(j * 32 + lane) < keep && !((uint32_t)k[j] & CONTRIB) && sc < gk;
+        if (__any_sync(FULL, want)) {
+            kth = contribute32(gbest_q, glock + qid, want ? sc : NOKEY, lane);
+            if (want) k[j] |= (uint64_t)CONTRIB;
+            gk = ld_relaxed_u32(gbest_q + GB - 1);
+        }
+    }
     __syncwarp();
 #pragma unroll
     for (int j = 0; j < PER; ++j) {
@@ -180,7 +263,8 @@ __device__ __noinline__ CompactOut compact_lane(int l, uint32_t my_cnt, float my
     if (lane == l) {
         out.cnt = keep;
         if (ovf) flags[my_qid] = 1u;                          // K4 re-solves this query exactly
-        const float mine = nextafterf(lim, __int_as_float(0x7f800000));
+        const float glim = okey_inv(kth) + margin;            // +inf while the global list holds fewer than K scores
+        const float mine = nextafterf(fminf(lim, glim), __int_as_float(0x7f800000));
         const float theirs = okey_inv(ld_relaxed_u32(&gthr[my_qid]));
         if (mine < theirs) atomicMin(&gthr[my_qid], okey(mine));
         out.thr = fminf(my_thr, fminf(mine, theirs));
@@ -239,12 +323,13 @@ void build_tensor_image(hvs_engine *e, int a)
 bool tensor_path_available() { return true; }
 
 // ---- the sweep --------------------------------------------------------------------------------------
+template <bool PIPE>
 __global__ void __launch_bounds__(NTHR, 1)
 k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slices, const TileItem *__restrict__ items,
               uint32_t n_items, const uint32_t *__restrict__ item_q, const unsigned char *__restrict__ img0,
               const unsigned char *__restrict__ img1, float xnorm_max, float sx, uint64_t *__restrict__ pool,
               uint64_t *__restrict__ cand, uint32_t *__restrict__ cand_cnt, uint32_t *__restrict__ gthr,
-              uint32_t *__restrict__ flags)
+              uint32_t *__restrict__ gbest, uint32_t *__restrict__ glock, uint32_t *__restrict__ flags)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TensorSmem &S = *reinterpret_cast<TensorSmem *>(smem_raw);
@@ -368,11 +453,12 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
                     const uint32_t u = ga[h] + t;
                     const int b = u & 1;
                     // room for a whole stage of survivors, and a look at what other CTAs found out
-                    uint32_t need = __ballot_sync(FULL, st.cnt > (uint32_t)(POOL - TN));
+                    uint32_t need = __ballot_sync(FULL, st.cnt > (uint32_t)(POOL - TN) ||
+                                                            (st.cnt >= (uint32_t)TN && st.thr == __int_as_float(0x7f800000)));
                     while (need) {
                         const int l = __ffs(need) - 1;
                         need &= need - 1;
-                        const CompactOut o = compact_lane(l, st.cnt, st.thr, st.margin, st.qid, pool_warp, gthr, flags, lane);
+                        const CompactOut o = compact_lane(l, st.cnt, st.thr, st.margin, st.qid, pool_warp, gthr, gbest, glock, flags, lane);
                         st.cnt = o.cnt; st.thr = o.thr;
                     }
                     if ((t & 7) == 7 && qslot < it.nq) st.thr = fminf(st.thr, okey_inv(ld_relaxed_u32(&gthr[st.qid])));
@@ -380,40 +466,73 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
                     tc_fence_after();
                     const uint32_t tcol = tlane + (uint32_t)(h * 2 + b) * TN;
                     const uint32_t trow0 = row0 + t * TN;
-#pragma unroll 1
-                    for (int c4 = 0; c4 < TN / 32; ++c4) {
-                        uint32_t r[32];
-                        tmem_ld32(tcol + c4 * 32, r);
-                        tmem_wait_ld();
-                        float m0 = fminf(__uint_as_float(r[0]), __uint_as_float(r[1]));
-                        float m1 = fminf(__uint_as_float(r[2]), __uint_as_float(r[3]));
+                    // 32 columns (data rows) at a time: four 8-wide minima, one compare; only a group whose minimum
+                    // beats the threshold is looked at element by element (room in the pool was made above)
+                    auto scan = [&](const uint32_t (&r)[32], uint32_t rbase) {
+                        float g[4];
 #pragma unroll
-                        for (int c = 4; c < 32; c += 4) {
-                            m0 = fminf(m0, fminf(__uint_as_float(r[c]), __uint_as_float(r[c + 1])));
-                            m1 = fminf(m1, fminf(__uint_as_float(r[c + 2]), __uint_as_float(r[c + 3])));
+                        for (int q4 = 0; q4 < 4; ++q4) {
+                            const float a0 = fminf(__uint_as_float(r[8 * q4 + 0]), __uint_as_float(r[8 * q4 + 1]));
+                            const float a1 = fminf(__uint_as_float(r[8 * q4 + 2]), __uint_as_float(r[8 * q4 + 3]));
+                            const float a2 = fminf(__uint_as_float(r[8 * q4 + 4]), __uint_as_float(r[8 * q4 + 5]));
+                            const float a3 = fminf(__uint_as_float(r[8 * q4 + 6]), __uint_as_float(r[8 * q4 + 7]));
+                            g[q4] = fminf(fminf(a0, a1), fminf(a2, a3));
                         }
-                        if (fminf(m0, m1) < st.thr) {
-                            // some of these 32 rows survive: append them to the pool (room was made above)
-                            const uint32_t rbase = trow0 + c4 * 32;
+                        if (fminf(fminf(g[0], g[1]), fminf(g[2], g[3])) < st.thr) {
 #pragma unroll
-                            for (int c = 0; c < 32; ++c) {
-                                const float s = __uint_as_float(r[c]);
-                                const uint32_t row = rbase + c;
-                                if (s < st.thr && row >= st.qlo && row < st.qhi)
-                                    mypool[st.cnt++] = ((uint64_t)okey(s) << 32) | row;
-                            }
+                            for (int q4 = 0; q4 < 4; ++q4)
+                                if (g[q4] < st.thr) {
+#pragma unroll
+                                    for (int c = 8 * q4; c < 8 * q4 + 8; ++c) {
+                                        const float s = __uint_as_float(r[c]);
+                                        const uint32_t row = rbase + c;
+                                        if (s < st.thr && row >= st.qlo && row < st.qhi)
+                                            mypool[st.cnt++] = ((uint64_t)okey(s) << 32) | row;
+                                    }
+                                }
+                        }
+                    };
+                    if (PIPE) {
+                        // two register sets: the TMEM load of the next 32 columns is in flight while these are scanned
+                        uint32_t ra[32], rb[32];
+                        tmem_ld32(tcol, ra);
+#pragma unroll 1
+                        for (int c4 = 0; c4 < TN / 32; c4 += 2) {
+                            tmem_wait_ld();
+                            tmem_ld32(tcol + (c4 + 1) * 32, rb);
+                            scan(ra, trow0 + c4 * 32);
+                            tmem_wait_ld();
+                            if (c4 + 2 < TN / 32) tmem_ld32(tcol + (c4 + 2) * 32, ra);
+                            scan(rb, trow0 + (c4 + 1) * 32);
+                        }
+                    } else {
+#pragma unroll 1
+                        for (int c4 = 0; c4 < TN / 32; ++c4) {
+                            uint32_t r[32];
+                            tmem_ld32(tcol + c4 * 32, r);
+                            tmem_wait_ld();
+                            scan(r, trow0 + c4 * 32);
                         }
                     }
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&S.tempty[h][b]);
                 }
-                // hand the pool to K5: lists need not be sorted, only short enough
-                uint32_t need = __ballot_sync(FULL, st.cnt > (uint32_t)KOUT);
+                // hand the pool to K5: lists need not be sorted, only short enough.  Pools that hold scores the
+                // global list has not seen are compacted too, so that the next items start with tight thresholds.
+                bool news = false;
+                if (st.cnt) {
+                    const uint32_t gk = ld_relaxed_u32(gbest + (size_t)st.qid * GB + GB - 1);
+                    for (uint32_t e = 0; e < st.cnt && !news; ++e) {
+                        const uint64_t kk = mypool[e];
+                        news = !((uint32_t)kk & CONTRIB) && (uint32_t)(kk >> 32) < gk;
+                    }
+                }
+                uint32_t need = __ballot_sync(FULL, st.cnt > (uint32_t)KOUT || news);
                 while (need) {
                     const int l = __ffs(need) - 1;
                     need &= need - 1;
-                    const CompactOut o = compact_lane(l, st.cnt, st.thr, st.margin, st.qid, pool_warp, gthr, flags, lane);
+                    const CompactOut o = compact_lane(l, st.cnt, st.thr, st.margin, st.qid, pool_warp, gthr, gbest, glock, flags, lane);
                     st.cnt = o.cnt; st.thr = o.thr;
                 }
                 for (int l = 0; l < 32; ++l) {
@@ -446,7 +565,8 @@ cudaError_t launch_tile_tensor(hvs_engine *e, const float *queries_dev, const QS
     static bool attr_done = false;
     const int smem = (int)sizeof(TensorSmem);
     if (!attr_done) {
-        cudaError_t c = cudaFuncSetAttribute(k_tile_tensor, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t c = cudaFuncSetAttribute(k_tile_tensor<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (c == cudaSuccess) c = cudaFuncSetAttribute(k_tile_tensor<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (c != cudaSuccess) return c;
         attr_done = true;
     }
@@ -454,10 +574,20 @@ cudaError_t launch_tile_tensor(hvs_engine *e, const float *queries_dev, const QS
     const uint32_t grid = n_items < (uint32_t)e->sm_count ? n_items : (uint32_t)e->sm_count;
     cudaError_t c = e->d_pool.ensure((size_t)e->sm_count * QT_TENSOR * POOL * 8);
     if (c != cudaSuccess) return c;
-    k_tile_tensor<<<grid, NTHR, smem, e->stream>>>(queries_dev, slices_dev, items_dev + item_begin, n_items, item_q_dev,
-                                                    ix.xb[0].as<unsigned char>(), ix.xb[1].as<unsigned char>(), ix.xnorm_max,
-                                                    ix.img_scale, e->d_pool.as<uint64_t>(), cand_dev, cand_cnt_dev, gthr_dev,
-                                                    flags_dev);
+    c = e->d_gbest.ensure((size_t)e->stats.m * GB * 4);
+    if (c != cudaSuccess) return c;
+    c = e->d_glock.ensure((size_t)e->stats.m * 4);
+    if (c != cudaSuccess) return c;
+    c = launch_fill_u32(e, e->d_gbest.as<uint32_t>(), 0xff800000u /* okey(+inf) */, (size_t)e->stats.m * GB);
+    if (c != cudaSuccess) return c;
+    c = cudaMemsetAsync(e->d_glock.p, 0, (size_t)e->stats.m * 4, e->stream);
+    if (c != cudaSuccess) return c;
+    static const bool pipe = [] { const char *v = getenv("HVS_K3_PIPE"); return v && v[0] == '1'; }();
+    auto kern = pipe ? k_tile_tensor<true> : k_tile_tensor<false>;
+    kern<<<grid, NTHR, smem, e->stream>>>(queries_dev, slices_dev, items_dev + item_begin, n_items, item_q_dev,
+                                          ix.xb[0].as<unsigned char>(), ix.xb[1].as<unsigned char>(), ix.xnorm_max, ix.img_scale,
+                                          e->d_pool.as<uint64_t>(), cand_dev, cand_cnt_dev, gthr_dev, e->d_gbest.as<uint32_t>(),
+                                          e->d_glock.as<uint32_t>(), flags_dev);
     return cudaGetLastError();
 }
 
