@@ -98,6 +98,18 @@ struct Plan {
     uint64_t pairs = 0, pairs_computed = 0, pairs_tile = 0;
     uint32_t n_lists = 0;
     uint32_t n_ffma = 0, n_tensor = 0;
+    // scratch kept between solves (fresh multi-megabyte vectors cost more in page faults than the planning)
+    struct Local { std::vector<TileItem> items; std::vector<uint32_t> item_q, cstart, cur, fill; uint64_t pairs_computed = 0; };
+    std::vector<Local> locals;
+    std::vector<uint64_t> sort_keys[2];
+    std::vector<uint32_t> order[2], nlist, qpos;
+    std::vector<uint8_t> is_tile;
+    void reset()
+    {
+        direct_q.clear(); items.clear(); item_q.clear(); tile_q.clear(); q_list_off.clear(); q_lists.clear();
+        pairs = pairs_computed = pairs_tile = 0;
+        n_lists = n_ffma = n_tensor = 0;
+    }
 };
 
 struct PlanParams {

@@ -5,7 +5,12 @@
 // keys of one arena (hvs_index.cu); the planner then buckets queries that share rows into
 // 128-query tile items, or sends sparse / tiny slices to the direct scan kernel.
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cmath>
+#include <thread>
 
 #include "hvs_engine.h"
 
@@ -97,10 +102,14 @@ cudaError_t launch_plan_search(hvs_engine *e, const float *queries_dev, uint32_t
 // comparator sorts over the incidence list.
 void plan_build(const QSlice *sl, uint32_t m, const PlanParams &pp, Plan &P)
 {
-    P = Plan();
+    static const bool dbg = getenv("HVS_PLAN_DEBUG") != nullptr;
+    auto T0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) { if (dbg) { auto t = std::chrono::steady_clock::now(); fprintf(stderr, "  plan %-14s %.2f ms\n", what, std::chrono::duration<double, std::milli>(t - T0).count()); T0 = t; } };
+    P.reset();
     const bool tensor = pp.tensor_available && (pp.mode == HVS_MODE_AUTO || pp.mode == HVS_MODE_TENSOR);
     const uint32_t BQ = tensor ? (uint32_t)QT_TENSOR : (uint32_t)QT;
-    std::vector<uint8_t> is_tile(m, 0);
+    std::vector<uint8_t> &is_tile = P.is_tile;
+    is_tile.assign(m, 0);
     uint64_t tile_qrows = 0;
     for (uint32_t i = 0; i < m; ++i) {
         uint32_t len = sl[i].end - sl[i].begin;
@@ -144,6 +153,7 @@ void plan_build(const QSlice *sl, uint32_t m, const PlanParams &pp, Plan &P)
         if (sl[x].begin != sl[y].begin) return sl[x].begin < sl[y].begin;
         return x < y;
     });
+    lap("classify");
     if (!tile_qrows) return;
 
     // chunk size: aim at ~16 items per SM over the whole job, power of two
@@ -152,38 +162,87 @@ void plan_build(const QSlice *sl, uint32_t m, const PlanParams &pp, Plan &P)
     while ((uint64_t)R * 2 <= want && R < pp.chunk_rows * 4u) R *= 2;
     if (R > (1u << 19)) R = 1u << 19;
 
-    std::vector<uint32_t> order, cstart, fill;
-    for (uint32_t a = 0; a < 2; ++a) {
-        // tile queries of this arena ordered by (begin, end, index): each chunk's batches then group
-        // queries with similar slices, which keeps the union of rows an item sweeps tight
-        order.clear();
-        uint32_t maxend = 0;
-        for (uint32_t i = 0; i < m; ++i)
-            if (is_tile[i] && sl[i].arena == a) { order.push_back(i); maxend = std::max(maxend, sl[i].end); }
-        if (order.empty()) continue;
-        std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
+    // ---- (chunk, query) incidences -> items.  Independent per (arena, block of chunks): host threads.
+    struct Task { uint32_t arena, c0, c1; };
+    using Local = Plan::Local;
+    std::vector<uint32_t> *order = P.order;
+    std::vector<Task> tasks;
+    uint64_t incid = 0;
+    unsigned nthreads = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 8u);
+    auto parallel = [&](size_t njobs, auto &&job) {
+        if (nthreads <= 1 || njobs <= 1) { for (size_t j = 0; j < njobs; ++j) job(j); return; }
+        std::atomic<size_t> next{0};
+        auto worker = [&]() { for (size_t j; (j = next.fetch_add(1)) < njobs;) job(j); };
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < nthreads && t < njobs; ++t) th.emplace_back(worker);
+        worker();
+        for (auto &t : th) t.join();
+    };
+    uint32_t maxend[2] = {0, 0};
+    for (uint32_t a = 0; a < 2; ++a) { order[a].clear(); P.sort_keys[a].clear(); }
+    for (uint32_t i = 0; i < m; ++i)
+        if (is_tile[i]) {
+            const uint32_t a = sl[i].arena;
+            order[a].push_back(i);
+            maxend[a] = std::max(maxend[a], sl[i].end);
+            incid += (sl[i].end - 1) / R - sl[i].begin / R + 1;
+        }
+    if (incid < 65536) nthreads = 1;
+    // tile queries of each arena ordered by (begin, end, index): each chunk's batches then group queries
+    // with similar slices, which keeps the union of rows an item sweeps tight
+    parallel(2, [&](size_t a) {
+        std::vector<uint32_t> &ord = order[a];
+        if (ord.empty()) return;
+        bool same = true;                                            // all slices equal (e.g. unfiltered queries): already ordered
+        for (size_t k = 1; k < ord.size() && same; ++k)
+            same = sl[ord[k]].begin == sl[ord[0]].begin && sl[ord[k]].end == sl[ord[0]].end;
+        if (same) return;
+        std::sort(ord.begin(), ord.end(), [&](uint32_t x, uint32_t y) {
             if (sl[x].begin != sl[y].begin) return sl[x].begin < sl[y].begin;
             if (sl[x].end != sl[y].end) return sl[x].end < sl[y].end;
             return x < y;
         });
-        const uint32_t nchunk = (maxend + R - 1) / R;
-        cstart.assign(nchunk + 1, 0);
-        for (uint32_t i : order)
-            for (uint32_t c = sl[i].begin / R; c <= (sl[i].end - 1) / R; ++c) ++cstart[c + 1];
-        for (uint32_t c = 0; c < nchunk; ++c) cstart[c + 1] += cstart[c];
-        fill.assign(cstart[nchunk], 0);
-        {
-            std::vector<uint32_t> cur(cstart.begin(), cstart.end() - 1);
-            for (uint32_t i : order)
-                for (uint32_t c = sl[i].begin / R; c <= (sl[i].end - 1) / R; ++c) fill[cur[c]++] = i;
+    });
+    for (uint32_t a = 0; a < 2; ++a) {
+        if (order[a].empty()) continue;
+        const uint32_t nchunk = (maxend[a] + R - 1) / R;
+        const uint32_t per = std::max(1u, (nchunk + 7) / 8);
+        for (uint32_t c = 0; c < nchunk; c += per) tasks.push_back({a, c, std::min(nchunk, c + per)});
+    }
+    std::vector<Local> &locals = P.locals;
+    if (locals.size() < tasks.size()) locals.resize(tasks.size());
+    auto run_task = [&](size_t ti) {
+        const Task tk = tasks[ti];
+        Local &L = locals[ti];
+        L.items.clear(); L.item_q.clear(); L.pairs_computed = 0;
+        const std::vector<uint32_t> &ord = order[tk.arena];
+        const uint32_t nc = tk.c1 - tk.c0;
+        std::vector<uint32_t> &cstart = L.cstart, &fill = L.fill, &cur = L.cur;
+        cstart.assign(nc + 1, 0);
+        auto range = [&](uint32_t i, uint32_t &lo, uint32_t &hi) {     // chunks of query i inside this task, [lo, hi)
+            lo = std::max(sl[i].begin / R, tk.c0);
+            hi = std::min((sl[i].end - 1) / R + 1, tk.c1);
+        };
+        for (uint32_t i : ord) {
+            uint32_t lo, hi;
+            range(i, lo, hi);
+            for (uint32_t c = lo; c < hi; ++c) ++cstart[c - tk.c0 + 1];
         }
-        for (uint32_t c = 0; c < nchunk; ++c) {
-            const uint32_t c0 = c * R;
+        for (uint32_t c = 0; c < nc; ++c) cstart[c + 1] += cstart[c];
+        fill.resize(cstart[nc]);
+        cur.assign(cstart.begin(), cstart.end() - 1);
+        for (uint32_t i : ord) {
+            uint32_t lo, hi;
+            range(i, lo, hi);
+            for (uint32_t c = lo; c < hi; ++c) fill[cur[c - tk.c0]++] = i;
+        }
+        for (uint32_t c = 0; c < nc; ++c) {
+            const uint32_t c0 = (tk.c0 + c) * R;
             const uint64_t c1 = (uint64_t)c0 + R;
             for (uint32_t t = cstart[c]; t < cstart[c + 1]; t += BQ) {
                 const uint32_t te = std::min(cstart[c + 1], t + BQ);
                 TileItem it{};
-                it.arena = a;
+                it.arena = tk.arena;
                 uint32_t lo = 0xffffffffu, hi = 0;
                 for (uint32_t k = t; k < te; ++k) {
                     lo = std::min(lo, std::max(sl[fill[k]].begin, c0));
@@ -191,30 +250,53 @@ void plan_build(const QSlice *sl, uint32_t m, const PlanParams &pp, Plan &P)
                 }
                 it.row_begin = lo; it.row_end = hi;
                 it.nq = te - t;
-                it.q_off = (uint32_t)P.item_q.size();
-                P.item_q.insert(P.item_q.end(), fill.begin() + t, fill.begin() + te);
+                it.q_off = (uint32_t)L.item_q.size();                 // rebased below
+                L.item_q.insert(L.item_q.end(), fill.begin() + t, fill.begin() + te);
                 it.kind = tensor ? 1u : 0u;
-                P.items.push_back(it);
-                P.pairs_computed += (uint64_t)(hi - lo) * it.nq;
+                L.items.push_back(it);
+                L.pairs_computed += (uint64_t)(hi - lo) * it.nq;
             }
         }
+    };
+    parallel(tasks.size(), run_task);
+    lap("incidences");
+    size_t n_items = 0, n_itemq = 0;
+    for (size_t ti = 0; ti < tasks.size(); ++ti) { n_items += locals[ti].items.size(); n_itemq += locals[ti].item_q.size(); }
+    P.items.reserve(n_items);
+    P.item_q.reserve(n_itemq);
+    for (size_t ti = 0; ti < tasks.size(); ++ti) {
+        Local &L = locals[ti];
+        const uint32_t base = (uint32_t)P.item_q.size();
+        for (auto it : L.items) { it.q_off += base; P.items.push_back(it); }
+        P.item_q.insert(P.item_q.end(), L.item_q.begin(), L.item_q.end());
+        P.pairs_computed += L.pairs_computed;
     }
+    lap("concat");
     // longest first (LPT); equal-cost items stay in (arena,row) order so that CTAs running
     // concurrently share the same rows in L2
     std::stable_sort(P.items.begin(), P.items.end(), [](const TileItem &x, const TileItem &y) {
         return (x.row_end - x.row_begin) > (y.row_end - y.row_begin);
     });
-    // candidate lists: item-major after sorting; CSR per tile query by counting
-    std::vector<uint32_t> nlist(m, 0);
+    // candidate lists: item-major after sorting; CSR per tile query by counting (order inside a query is irrelevant)
+    std::vector<uint32_t> &nlist = P.nlist, &qpos = P.qpos;
+    nlist.assign(m, 0);
     uint32_t off = 0;
     for (auto &it : P.items) {
         it.out_off = off;
-        for (uint32_t s = 0; s < it.nq; ++s) ++nlist[P.item_q[it.q_off + s]];
         off += it.nq;
         if (it.kind) ++P.n_tensor; else ++P.n_ffma;
     }
     P.n_lists = off;
-    std::vector<uint32_t> qpos(m, 0);
+    // every thread owns a range of query indices and scans all (item, slot) pairs: no atomics, sequential reads
+    const size_t nrange = nthreads > 1 ? nthreads : 1;
+    auto qrange = [&](size_t r, uint32_t &q0, uint32_t &q1) { q0 = (uint32_t)((uint64_t)m * r / nrange); q1 = (uint32_t)((uint64_t)m * (r + 1) / nrange); };
+    parallel(nrange, [&](size_t r) {
+        uint32_t q0, q1;
+        qrange(r, q0, q1);
+        for (uint32_t q : P.item_q) if (q >= q0 && q < q1) ++nlist[q];
+    });
+    lap("nlist");
+    qpos.assign(m, 0);
     P.q_list_off.push_back(0);
     for (uint32_t i = 0; i < m; ++i)
         if (is_tile[i]) {
@@ -223,8 +305,18 @@ void plan_build(const QSlice *sl, uint32_t m, const PlanParams &pp, Plan &P)
             P.q_list_off.push_back(qpos[i] + nlist[i]);
         }
     P.q_lists.resize(P.q_list_off.back());
-    for (const auto &it : P.items)
-        for (uint32_t s = 0; s < it.nq; ++s) P.q_lists[qpos[P.item_q[it.q_off + s]]++] = it.out_off + s;
+    parallel(nrange, [&](size_t r) {
+        uint32_t q0, q1;
+        qrange(r, q0, q1);
+        for (const TileItem &it : P.items) {
+            const uint32_t *iq = P.item_q.data() + it.q_off;
+            for (uint32_t s = 0; s < it.nq; ++s) {
+                const uint32_t q = iq[s];
+                if (q >= q0 && q < q1) P.q_lists[qpos[q]++] = it.out_off + s;
+            }
+        }
+    });
+    lap("q_lists");
 }
 
 }  // namespace hvs
@@ -242,7 +334,7 @@ extern "C" int hvs_plan_dryrun(const uint32_t *arena, const uint32_t *begin, con
     hvs::PlanParams pp;
     pp.mode = mode;
     pp.tensor_available = (mode == HVS_MODE_TENSOR || mode == HVS_MODE_AUTO);
-    hvs::Plan P;
+    static thread_local hvs::Plan P;   // keeps its scratch between calls, like the engine's plan
     hvs::plan_build(sl.data(), m, pp, P);
     for (uint32_t i = 0; i < m; ++i) out_kind[i] = 1;
     for (uint32_t q : P.direct_q) out_kind[q] = 0;

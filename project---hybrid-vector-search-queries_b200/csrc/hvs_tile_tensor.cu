@@ -44,9 +44,9 @@ constexpr int KP = 112;               // padded contraction length (7 MMA k-step
 constexpr int KU = KP / 8;            // 16-byte units per row
 constexpr int GROUP_B = KU * 128;     // bytes per 8-row group of the image (1792)
 constexpr int ROW_B = KP * 2;         // bytes per row (224)
-constexpr int TN = 128;               // data rows per stage == MMA N
-constexpr int NST = 5;                // B stages in flight
-constexpr int STAGE_B = TN * ROW_B;   // 28,672
+constexpr int TN = 256;               // data rows per stage == MMA N
+constexpr int NST = 3;                // B stages in flight
+constexpr int STAGE_B = TN * ROW_B;   // 57,344
 constexpr int A_B = 128 * ROW_B;      // one query half
 constexpr int NTHR = 320;
 constexpr int POOL = TENSOR_POOL;     // survivor pool entries per query (global memory)
@@ -57,13 +57,13 @@ constexpr uint32_t ROW_MASK = 0x7fffffffu, CONTRIB = 0x80000000u;   // top bit o
 constexpr uint32_t NOKEY = 0xffffffffu;
 
 static_assert(QT_TENSOR == 256, "two M=128 halves");
-static_assert(POOL == 512 && KOUT <= POOL - TN, "pool must take a whole stage after a compaction");
+static_assert(POOL == 512 && KOUT <= POOL - 32, "pool must take 32 more survivors after a compaction");
 
 struct TensorSmem {
     alignas(128) unsigned char b[NST][STAGE_B];
     alignas(128) unsigned char a[2][A_B];
     alignas(8) uint64_t full[NST], empty[NST];
-    alignas(8) uint64_t tfull[2][2], tempty[2][2];
+    alignas(8) uint64_t tfull[2], tempty[2];
     uint32_t tmem_base;
 };
 
@@ -107,6 +107,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
           "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
+}
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t p;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(p));
+    return p != 0;
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -273,6 +279,41 @@ __device__ __noinline__ CompactOut compact_lane(int l, uint32_t my_cnt, float my
     return out;
 }
 
+// Warp-cooperative, item end: tell the query's global list about pool entries it has not seen (no sort).
+// Returns the (possibly tightened) threshold for lane `l`.
+__device__ __noinline__ float contribute_pool(int l, uint32_t my_cnt, float my_thr, float my_margin, uint32_t my_qid,
+                                              uint64_t *__restrict__ pool_warp, uint32_t *__restrict__ gthr,
+                                              uint32_t *__restrict__ gbest, uint32_t *__restrict__ glock, int lane)
+{
+    const uint32_t n = __shfl_sync(FULL, my_cnt, l);
+    const float margin = __shfl_sync(FULL, my_margin, l);
+    const uint32_t qid = __shfl_sync(FULL, my_qid, l);
+    uint64_t *P = pool_warp + (size_t)l * POOL;
+    uint32_t *gbest_q = gbest + (size_t)qid * GB;
+    uint32_t gk = ld_relaxed_u32(gbest_q + GB - 1);
+    uint32_t kth = NOKEY;
+    for (uint32_t base = 0; base < n; base += 32) {
+        const uint32_t e = base + lane;
+        const uint64_t kk = e < n ? P[e] : KEY_INF;
+        const uint32_t sc = (uint32_t)(kk >> 32);
+        const bool want = e < n && !((uint32_t)kk & CONTRIB) && sc < gk;
+        if (__any_sync(FULL, want)) {
+            kth = contribute32(gbest_q, glock + qid, want ? sc : NOKEY, lane);
+            if (want) P[e] = kk | (uint64_t)CONTRIB;
+            gk = ld_relaxed_u32(gbest_q + GB - 1);
+        }
+    }
+    float thr = my_thr;
+    if (lane == l && kth != NOKEY) {
+        const float mine = nextafterf(okey_inv(kth) + margin, __int_as_float(0x7f800000));
+        const float theirs = okey_inv(ld_relaxed_u32(&gthr[my_qid]));
+        if (mine < theirs) atomicMin(&gthr[my_qid], okey(mine));
+        thr = fminf(my_thr, fminf(mine, theirs));
+    }
+    __syncwarp();
+    return thr;
+}
+
 }  // namespace
 
 // ---- FP16 image of an arena ------------------------------------------------------------------------
@@ -329,7 +370,7 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
               uint32_t n_items, const uint32_t *__restrict__ item_q, const unsigned char *__restrict__ img0,
               const unsigned char *__restrict__ img1, float xnorm_max, float sx, uint64_t *__restrict__ pool,
               uint64_t *__restrict__ cand, uint32_t *__restrict__ cand_cnt, uint32_t *__restrict__ gthr,
-              uint32_t *__restrict__ gbest, uint32_t *__restrict__ glock, uint32_t *__restrict__ flags)
+              uint32_t *__restrict__ gbest, uint32_t *__restrict__ glock, uint32_t *__restrict__ flags, int dbg)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TensorSmem &S = *reinterpret_cast<TensorSmem *>(smem_raw);
@@ -337,8 +378,7 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
 
     if (tid == 0) {
         for (int s = 0; s < NST; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
-        for (int h = 0; h < 2; ++h)
-            for (int b = 0; b < 2; ++b) { mbar_init(&S.tfull[h][b], 1); mbar_init(&S.tempty[h][b], 4); }
+        for (int h = 0; h < 2; ++h) { mbar_init(&S.tfull[h], 1); mbar_init(&S.tempty[h], 4); }
         mbar_fence_init();
     }
     if (warp == 1) {                                                  // TMEM: all 512 columns, this warp owns them
@@ -390,43 +430,48 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
         __syncthreads();
 
         if (warp == 0) {
-            // ===== TMA producer =====
-            if (lane == 0) {
-                const unsigned char *src = img + (size_t)(row0 >> 3) * GROUP_B;
-                for (uint32_t t = 0; t < ntiles; ++t) {
-                    const uint32_t g = gt + t;
-                    const int st = g % NST;
-                    mbar_wait(&S.empty[st], ((g / NST) & 1) ^ 1);
+            // ===== TMA producer (whole warp runs the loop, one elected lane talks to the TMA engine) =====
+            const unsigned char *src = img + (size_t)(row0 >> 3) * GROUP_B;
+            for (uint32_t t = 0; t < ntiles; ++t) {
+                const uint32_t g = gt + t;
+                const int st = g % NST;
+                mbar_wait(&S.empty[st], ((g / NST) & 1) ^ 1);
+                if (elect_one()) {
                     mbar_expect_tx(&S.full[st], STAGE_B);
                     bulk_g2s(S.b[st], src + (size_t)t * STAGE_B, STAGE_B, &S.full[st]);
                 }
+                __syncwarp();
             }
-            __syncwarp();
         } else if (warp == 1) {
-            // ===== MMA issuer =====
-            if (lane == 0) {
-                const uint64_t adesc[2] = {smem_desc(smem_u32(S.a[0])), smem_desc(smem_u32(S.a[1]))};
-                for (uint32_t t = 0; t < ntiles; ++t) {
-                    const uint32_t g = gt + t;
-                    const int st = g % NST;
-                    mbar_wait(&S.full[st], (g / NST) & 1);
-                    tc_fence_after();
-                    const uint64_t bdesc = smem_desc(smem_u32(S.b[st]));
-                    for (int h = 0; h < nhalf; ++h) {
-                        const uint32_t u = ga[h] + t;
-                        const int b = u & 1;
-                        mbar_wait(&S.tempty[h][b], ((u >> 1) & 1) ^ 1);  // epilogue drained this accumulator
-                        tc_fence_after();
-                        const uint32_t d = tmem + (uint32_t)(h * 2 + b) * TN;
+            // ===== MMA issuer: warp-uniform control flow, one elected lane issues =====
+            // Accumulator of half h = TMEM columns [256 h, 256 h + 256).  While the epilogue drains half 0 the
+            // tensor core works on half 1 of the same stage, and vice versa.
+            const uint64_t adesc0 = smem_desc(smem_u32(S.a[0])), adesc1 = smem_desc(smem_u32(S.a[1]));
+            for (uint32_t t = 0; t < ntiles; ++t) {
+                const uint32_t g = gt + t;
+                const int st = g % NST;
+                mbar_wait(&S.full[st], (g / NST) & 1);
+                const uint64_t bdesc = smem_desc(smem_u32(S.b[st]));
 #pragma unroll
-                        for (int j = 0; j < KP / 16; ++j)                // one k-step = two 16-byte units = 256 bytes
-                            tc_mma(d, adesc[h] + (uint64_t)(j * 16), bdesc + (uint64_t)(j * 16), IDESC, j > 0);
-                        tc_commit(&S.tfull[h][b]);
+                for (int h = 0; h < 2; ++h) {
+                    if (h < nhalf) {
+                        const uint32_t u = ga[h] + t;
+                        mbar_wait(&S.tempty[h], (u & 1) ^ 1);            // epilogue drained this accumulator
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint32_t d = tmem + (uint32_t)h * TN;
+                            const uint64_t ad = h ? adesc1 : adesc0;
+#pragma unroll
+                            for (int j = 0; j < KP / 16; ++j)            // one k-step = two 16-byte units = 256 bytes
+                                tc_mma(d, ad + (uint64_t)(j * 16), bdesc + (uint64_t)(j * 16), IDESC, j > 0);
+                            tc_commit(&S.tfull[h]);
+                        }
+                        __syncwarp();
                     }
-                    tc_commit(&S.empty[st]);                            // stage may be refilled once these MMAs retire
                 }
+                if (elect_one()) tc_commit(&S.empty[st]);               // stage may be refilled once these MMAs retire
+                __syncwarp();
             }
-            __syncwarp();
         } else {
             // ===== epilogue: one thread = one query =====
             const int ew = warp - 2, h = ew >> 2, quad = warp & 3;
@@ -448,78 +493,101 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
                     // -2 sx q must be representable in fp16: otherwise this query cannot use the tensor path
                     if (!(2.f * sx * sqrtf(sl.qnorm) < 60000.f)) { st.thr = __int_as_float(0xff800000); flags[st.qid] = 1u; }
                 }
-                const uint32_t tlane = tmem + ((uint32_t)(quad * 32) << 16);
-                for (uint32_t t = 0; t < ntiles; ++t) {
-                    const uint32_t u = ga[h] + t;
-                    const int b = u & 1;
-                    // room for a whole stage of survivors, and a look at what other CTAs found out
-                    uint32_t need = __ballot_sync(FULL, st.cnt > (uint32_t)(POOL - TN) ||
-                                                            (st.cnt >= (uint32_t)TN && st.thr == __int_as_float(0x7f800000)));
+                const uint32_t tcol = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)h * TN;
+                // 32 columns (data rows) at a time: four 8-wide minima, one compare; only a group whose minimum
+                // beats the threshold is looked at element by element
+                auto scan = [&](const uint32_t (&r)[32], uint32_t rbase) {
+                    float g[4];
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        const float a0 = fminf(__uint_as_float(r[8 * q4 + 0]), __uint_as_float(r[8 * q4 + 1]));
+                        const float a1 = fminf(__uint_as_float(r[8 * q4 + 2]), __uint_as_float(r[8 * q4 + 3]));
+                        const float a2 = fminf(__uint_as_float(r[8 * q4 + 4]), __uint_as_float(r[8 * q4 + 5]));
+                        const float a3 = fminf(__uint_as_float(r[8 * q4 + 6]), __uint_as_float(r[8 * q4 + 7]));
+                        g[q4] = fminf(fminf(a0, a1), fminf(a2, a3));
+                    }
+                    if (fminf(fminf(g[0], g[1]), fminf(g[2], g[3])) < st.thr) {
+#pragma unroll
+                        for (int q4 = 0; q4 < 4; ++q4)
+                            if (g[q4] < st.thr) {
+#pragma unroll
+                                for (int c = 8 * q4; c < 8 * q4 + 8; ++c) {
+                                    const float s = __uint_as_float(r[c]);
+                                    const uint32_t row = rbase + c;
+                                    if (s < st.thr && row >= st.qlo && row < st.qhi)
+                                        mypool[st.cnt++] = ((uint64_t)okey(s) << 32) | row;
+                                }
+                            }
+                    }
+                };
+                // room for 32 more survivors in every pool of this warp (else: sort, keep, tighten)
+                auto make_room = [&]() {
+                    uint32_t need = __ballot_sync(FULL, st.cnt > (uint32_t)(POOL - 32) ||
+                                                            (st.cnt >= 128u && st.thr == __int_as_float(0x7f800000)));
                     while (need) {
                         const int l = __ffs(need) - 1;
                         need &= need - 1;
                         const CompactOut o = compact_lane(l, st.cnt, st.thr, st.margin, st.qid, pool_warp, gthr, gbest, glock, flags, lane);
                         st.cnt = o.cnt; st.thr = o.thr;
                     }
-                    if ((t & 7) == 7 && qslot < it.nq) st.thr = fminf(st.thr, okey_inv(ld_relaxed_u32(&gthr[st.qid])));
-                    mbar_wait(&S.tfull[h][b], (u >> 1) & 1);
+                };
+                for (uint32_t t = 0; t < ntiles; ++t) {
+                    const uint32_t u = ga[h] + t;
+                    // a look at what other CTAs found out about this query
+                    if ((t & 3) == 3 && qslot < it.nq) st.thr = fminf(st.thr, okey_inv(ld_relaxed_u32(&gthr[st.qid])));
+                    mbar_wait(&S.tfull[h], u & 1);
                     tc_fence_after();
-                    const uint32_t tcol = tlane + (uint32_t)(h * 2 + b) * TN;
                     const uint32_t trow0 = row0 + t * TN;
-                    // 32 columns (data rows) at a time: four 8-wide minima, one compare; only a group whose minimum
-                    // beats the threshold is looked at element by element (room in the pool was made above)
-                    auto scan = [&](const uint32_t (&r)[32], uint32_t rbase) {
-                        float g[4];
-#pragma unroll
-                        for (int q4 = 0; q4 < 4; ++q4) {
-                            const float a0 = fminf(__uint_as_float(r[8 * q4 + 0]), __uint_as_float(r[8 * q4 + 1]));
-                            const float a1 = fminf(__uint_as_float(r[8 * q4 + 2]), __uint_as_float(r[8 * q4 + 3]));
-                            const float a2 = fminf(__uint_as_float(r[8 * q4 + 4]), __uint_as_float(r[8 * q4 + 5]));
-                            const float a3 = fminf(__uint_as_float(r[8 * q4 + 6]), __uint_as_float(r[8 * q4 + 7]));
-                            g[q4] = fminf(fminf(a0, a1), fminf(a2, a3));
-                        }
-                        if (fminf(fminf(g[0], g[1]), fminf(g[2], g[3])) < st.thr) {
-#pragma unroll
-                            for (int q4 = 0; q4 < 4; ++q4)
-                                if (g[q4] < st.thr) {
-#pragma unroll
-                                    for (int c = 8 * q4; c < 8 * q4 + 8; ++c) {
-                                        const float s = __uint_as_float(r[c]);
-                                        const uint32_t row = rbase + c;
-                                        if (s < st.thr && row >= st.qlo && row < st.qhi)
-                                            mypool[st.cnt++] = ((uint64_t)okey(s) << 32) | row;
-                                    }
-                                }
-                        }
-                    };
                     if (PIPE) {
                         // two register sets: the TMEM load of the next 32 columns is in flight while these are scanned
                         uint32_t ra[32], rb[32];
                         tmem_ld32(tcol, ra);
 #pragma unroll 1
                         for (int c4 = 0; c4 < TN / 32; c4 += 2) {
+                            make_room();
                             tmem_wait_ld();
                             tmem_ld32(tcol + (c4 + 1) * 32, rb);
                             scan(ra, trow0 + c4 * 32);
+                            make_room();
                             tmem_wait_ld();
                             if (c4 + 2 < TN / 32) tmem_ld32(tcol + (c4 + 2) * 32, ra);
                             scan(rb, trow0 + (c4 + 1) * 32);
                         }
-                    } else {
+                    } else if (dbg == 0) {
+#pragma unroll 1
+                        for (int c4 = 0; c4 < TN / 32; ++c4) {
+                            uint32_t r[32];
+                            tmem_ld32(tcol + c4 * 32, r);
+                            make_room();
+                            tmem_wait_ld();
+                            scan(r, trow0 + c4 * 32);
+                        }
+                    } else if (dbg == 2) {          // measurement only: TMEM loads, no scan (results are wrong)
 #pragma unroll 1
                         for (int c4 = 0; c4 < TN / 32; ++c4) {
                             uint32_t r[32];
                             tmem_ld32(tcol + c4 * 32, r);
                             tmem_wait_ld();
-                            scan(r, trow0 + c4 * 32);
+                            uint32_t x = 0;
+#pragma unroll
+                            for (int c = 0; c < 32; ++c) x ^= r[c];
+                            if (x == 0x12345678u) st.cnt++;
                         }
-                    }
+                    }                               // dbg == 1: measurement only, accumulators are not even read
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&S.tempty[h][b]);
+                    if (lane == 0) mbar_arrive(&S.tempty[h]);
                 }
-                // hand the pool to K5: lists need not be sorted, only short enough.  Pools that hold scores the
-                // global list has not seen are compacted too, so that the next items start with tight thresholds.
+                // hand the pool to K5: lists need not be sorted, only short enough
+                uint32_t need = __ballot_sync(FULL, st.cnt > (uint32_t)KOUT);
+                while (need) {
+                    const int l = __ffs(need) - 1;
+                    need &= need - 1;
+                    const CompactOut o = compact_lane(l, st.cnt, st.thr, st.margin, st.qid, pool_warp, gthr, gbest, glock, flags, lane);
+                    st.cnt = o.cnt; st.thr = o.thr;
+                }
+                // pools that hold scores the global list has not seen pass them on, so that the next items of
+                // these queries (other row chunks) start with tight thresholds
                 bool news = false;
                 if (st.cnt) {
                     const uint32_t gk = ld_relaxed_u32(gbest + (size_t)st.qid * GB + GB - 1);
@@ -528,12 +596,11 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
                         news = !((uint32_t)kk & CONTRIB) && (uint32_t)(kk >> 32) < gk;
                     }
                 }
-                uint32_t need = __ballot_sync(FULL, st.cnt > (uint32_t)KOUT || news);
+                need = __ballot_sync(FULL, news);
                 while (need) {
                     const int l = __ffs(need) - 1;
                     need &= need - 1;
-                    const CompactOut o = compact_lane(l, st.cnt, st.thr, st.margin, st.qid, pool_warp, gthr, gbest, glock, flags, lane);
-                    st.cnt = o.cnt; st.thr = o.thr;
+                    st.thr = contribute_pool(l, st.cnt, st.thr, st.margin, st.qid, pool_warp, gthr, gbest, glock, lane);
                 }
                 for (int l = 0; l < 32; ++l) {
                     const uint32_t c = __shfl_sync(FULL, st.cnt, l);
@@ -583,11 +650,12 @@ cudaError_t launch_tile_tensor(hvs_engine *e, const float *queries_dev, const QS
     c = cudaMemsetAsync(e->d_glock.p, 0, (size_t)e->stats.m * 4, e->stream);
     if (c != cudaSuccess) return c;
     static const bool pipe = [] { const char *v = getenv("HVS_K3_PIPE"); return v && v[0] == '1'; }();
+    static const int dbg = [] { const char *v = getenv("HVS_K3_DBG"); return v ? atoi(v) : 0; }();
     auto kern = pipe ? k_tile_tensor<true> : k_tile_tensor<false>;
     kern<<<grid, NTHR, smem, e->stream>>>(queries_dev, slices_dev, items_dev + item_begin, n_items, item_q_dev,
                                           ix.xb[0].as<unsigned char>(), ix.xb[1].as<unsigned char>(), ix.xnorm_max, ix.img_scale,
                                           e->d_pool.as<uint64_t>(), cand_dev, cand_cnt_dev, gthr_dev, e->d_gbest.as<uint32_t>(),
-                                          e->d_glock.as<uint32_t>(), flags_dev);
+                                          e->d_glock.as<uint32_t>(), flags_dev, dbg);
     return cudaGetLastError();
 }
 
