@@ -44,9 +44,9 @@ constexpr int KP = 112;               // padded contraction length (7 MMA k-step
 constexpr int KU = KP / 8;            // 16-byte units per row
 constexpr int GROUP_B = KU * 128;     // bytes per 8-row group of the image (1792)
 constexpr int ROW_B = KP * 2;         // bytes per row (224)
-constexpr int TN = 256;               // data rows per stage == MMA N
-constexpr int NST = 3;                // B stages in flight
-constexpr int STAGE_B = TN * ROW_B;   // 57,344
+constexpr int TN = 128;               // data rows per stage == MMA N
+constexpr int NST = 6;                // B stages in flight
+constexpr int STAGE_B = TN * ROW_B;   // 28,672
 constexpr int A_B = 128 * ROW_B;      // one query half
 constexpr int NTHR = 320;
 constexpr int POOL = TENSOR_POOL;     // survivor pool entries per query (global memory)
@@ -63,7 +63,7 @@ struct TensorSmem {
     alignas(128) unsigned char b[NST][STAGE_B];
     alignas(128) unsigned char a[2][A_B];
     alignas(8) uint64_t full[NST], empty[NST];
-    alignas(8) uint64_t tfull[2], tempty[2];
+    alignas(8) uint64_t tfull[2][2], tempty[2][2];
     uint32_t tmem_base;
 };
 
@@ -378,7 +378,8 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
 
     if (tid == 0) {
         for (int s = 0; s < NST; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
-        for (int h = 0; h < 2; ++h) { mbar_init(&S.tfull[h], 1); mbar_init(&S.tempty[h], 4); }
+        for (int h = 0; h < 2; ++h)
+            for (int b = 0; b < 2; ++b) { mbar_init(&S.tfull[h][b], 1); mbar_init(&S.tempty[h][b], 4); }
         mbar_fence_init();
     }
     if (warp == 1) {                                                  // TMEM: all 512 columns, this warp owns them
@@ -444,8 +445,8 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
             }
         } else if (warp == 1) {
             // ===== MMA issuer: warp-uniform control flow, one elected lane issues =====
-            // Accumulator of half h = TMEM columns [256 h, 256 h + 256).  While the epilogue drains half 0 the
-            // tensor core works on half 1 of the same stage, and vice versa.
+            // Accumulator (half h, buffer b) = TMEM columns [128 (2h+b), +128): the epilogue drains buffer b of
+            // a half while the tensor core fills buffer b^1 with the next stage.
             const uint64_t adesc0 = smem_desc(smem_u32(S.a[0])), adesc1 = smem_desc(smem_u32(S.a[1]));
             for (uint32_t t = 0; t < ntiles; ++t) {
                 const uint32_t g = gt + t;
@@ -456,15 +457,16 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
                 for (int h = 0; h < 2; ++h) {
                     if (h < nhalf) {
                         const uint32_t u = ga[h] + t;
-                        mbar_wait(&S.tempty[h], (u & 1) ^ 1);            // epilogue drained this accumulator
+                        const int b = u & 1;
+                        mbar_wait(&S.tempty[h][b], ((u >> 1) & 1) ^ 1);  // epilogue drained this accumulator
                         tc_fence_after();
                         if (elect_one()) {
-                            const uint32_t d = tmem + (uint32_t)h * TN;
+                            const uint32_t d = tmem + (uint32_t)(h * 2 + b) * TN;
                             const uint64_t ad = h ? adesc1 : adesc0;
 #pragma unroll
                             for (int j = 0; j < KP / 16; ++j)            // one k-step = two 16-byte units = 256 bytes
                                 tc_mma(d, ad + (uint64_t)(j * 16), bdesc + (uint64_t)(j * 16), IDESC, j > 0);
-                            tc_commit(&S.tfull[h]);
+                            tc_commit(&S.tfull[h][b]);
                         }
                         __syncwarp();
                     }
@@ -493,7 +495,7 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
                     // -2 sx q must be representable in fp16: otherwise this query cannot use the tensor path
                     if (!(2.f * sx * sqrtf(sl.qnorm) < 60000.f)) { st.thr = __int_as_float(0xff800000); flags[st.qid] = 1u; }
                 }
-                const uint32_t tcol = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)h * TN;
+                const uint32_t tlane = tmem + ((uint32_t)(quad * 32) << 16);
                 // 32 columns (data rows) at a time: four 8-wide minima, one compare; only a group whose minimum
                 // beats the threshold is looked at element by element
                 auto scan = [&](const uint32_t (&r)[32], uint32_t rbase) {
@@ -534,9 +536,11 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
                 for (uint32_t t = 0; t < ntiles; ++t) {
                     const uint32_t u = ga[h] + t;
                     // a look at what other CTAs found out about this query
-                    if ((t & 3) == 3 && qslot < it.nq) st.thr = fminf(st.thr, okey_inv(ld_relaxed_u32(&gthr[st.qid])));
-                    mbar_wait(&S.tfull[h], u & 1);
+                    if ((t & 7) == 7 && qslot < it.nq) st.thr = fminf(st.thr, okey_inv(ld_relaxed_u32(&gthr[st.qid])));
+                    const int b = u & 1;
+                    mbar_wait(&S.tfull[h][b], (u >> 1) & 1);
                     tc_fence_after();
+                    const uint32_t tcol = tlane + (uint32_t)(h * 2 + b) * TN;
                     const uint32_t trow0 = row0 + t * TN;
                     if (PIPE) {
                         // two register sets: the TMEM load of the next 32 columns is in flight while these are scanned
@@ -576,7 +580,7 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
                     }                               // dbg == 1: measurement only, accumulators are not even read
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&S.tempty[h]);
+                    if (lane == 0) mbar_arrive(&S.tempty[h][b]);
                 }
                 // hand the pool to K5: lists need not be sorted, only short enough
                 uint32_t need = __ballot_sync(FULL, st.cnt > (uint32_t)KOUT);
