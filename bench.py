@@ -294,6 +294,16 @@ def run_b200(args, rank, world, local_rank):
                    "peak_source": f"FFMA microkernel measured in this run at {peak_mhz:.0f} MHz (MEASURED_PEAKS.json has no FP32 figure); "
                                   f"nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.5", "frac_of_nominal": a / 74.5,
                    "traffic": None, "algorithmic_flop_per_launch": flops_tile, "ms_per_launch": st["ms_tile_ffma"]}
+    rl_tensor = None
+    if st["ms_tile_tensor"] > 0:
+        a = flops_tile / (st["ms_tile_tensor"] * 1e-3) / 1e12
+        tpeak, tsrc = (peaks["bf16_tflops_sustained"], "MEASURED_PEAKS.json bf16_tflops_sustained (measured; fp16 and bf16 share the tensor pipe rate)") \
+            if "bf16_tflops_sustained" in peaks else (1400.0, "fallback 1.4 PFLOP/s sustained")
+        rl_tensor = {"kernel": "k_tile_tensor", "bound": "tensor", "achieved": a, "peak": tpeak, "unit": "TFLOP/s", "frac": a / tpeak,
+                     "peak_source": tsrc, "traffic": None, "algorithmic_flop_per_launch": flops_tile,
+                     "issued_flop_per_launch": 2.0 * 112.0 * st["pairs_computed"], "ms_per_launch": st["ms_tile_tensor"],
+                     "note": "algorithmic = 200 flop per (query,row) pair (SURVEY 8d); the MMA issues K=112 (100 dims + 3 norm terms + pad) "
+                             "on every pair-slot of a 256-query x 128-row tile"}
     rl_direct = None
     if st["ms_direct"] > 0:
         b = 400.0 * st["pairs_direct"]                  # B_pair: 400 B per pair, no reuse
@@ -301,10 +311,9 @@ def run_b200(args, rank, world, local_rank):
         rl_direct = {"kernel": "k_direct", "bound": "hbm", "achieved": a, "peak": hbm_peak, "unit": "GB/s", "frac": a / hbm_peak,
                      "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({hbm_src})", "traffic": None,
                      "algorithmic_bytes_per_launch": b, "ms_per_launch": st["ms_direct"]}
-    roofline = rl_ffma if dom.startswith("K2") or rl_direct is None else rl_direct
-    if dom.startswith("K4") and rl_direct:
-        roofline = rl_direct
-    others = [r for r in (rl_ffma, rl_direct) if r is not None and r is not roofline]
+    by_kernel = {"K2": rl_ffma, "K3": rl_tensor, "K4": rl_direct}
+    roofline = by_kernel.get(dom[:2]) or rl_tensor or rl_ffma or rl_direct
+    others = [r for r in (rl_ffma, rl_tensor, rl_direct) if r is not None and r is not roofline]
 
     line = {"metric": "queries/sec", "value": world * m / (ms_step * 1e-3), "unit": "queries/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",

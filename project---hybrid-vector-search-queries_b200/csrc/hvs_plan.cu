@@ -157,10 +157,11 @@ void plan_build(const QSlice *sl, uint32_t m, const PlanParams &pp, Plan &P)
     if (!tile_qrows) return;
 
     // chunk size: aim at ~16 items per SM over the whole job, power of two
-    uint64_t want = tile_qrows / ((uint64_t)BQ * 16 * 148);
+    static const uint32_t ips = [] { const char *v = getenv("HVS_ITEMS_PER_SM"); int k = v ? atoi(v) : 0; return (uint32_t)(k > 0 ? k : 16); }();
+    uint64_t want = tile_qrows / ((uint64_t)BQ * ips * 148);
     uint32_t R = 8192;
-    while ((uint64_t)R * 2 <= want && R < pp.chunk_rows * 4u) R *= 2;
-    if (R > (1u << 19)) R = 1u << 19;
+    while ((uint64_t)R * 2 <= want) R *= 2;
+    if (R > (1u << 22)) R = 1u << 22;
 
     // ---- (chunk, query) incidences -> items.  Independent per (arena, block of chunks): host threads.
     struct Task { uint32_t arena, c0, c1; };
