@@ -288,14 +288,14 @@ def run_b200(args, rank, world, local_rank):
     dom = max(kern, key=kern.get)
     flops_tile = 200.0 * st["pairs_tile"]              # 200 flop per (query,row) pair
     rl_ffma = None
-    if st["ms_tile_ffma"] > 0:
+    if st["n_items_ffma"] > 0 and st["ms_tile_ffma"] > 0:
         a = flops_tile / (st["ms_tile_ffma"] * 1e-3) / 1e12
         rl_ffma = {"kernel": "k_tile_ffma", "bound": "fp32", "achieved": a, "peak": peak_tf, "unit": "TFLOP/s", "frac": a / peak_tf,
                    "peak_source": f"FFMA microkernel measured in this run at {peak_mhz:.0f} MHz (MEASURED_PEAKS.json has no FP32 figure); "
                                   f"nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.5", "frac_of_nominal": a / 74.5,
                    "traffic": None, "algorithmic_flop_per_launch": flops_tile, "ms_per_launch": st["ms_tile_ffma"]}
     rl_tensor = None
-    if st["ms_tile_tensor"] > 0:
+    if st["n_items_tensor"] > 0 and st["ms_tile_tensor"] > 0:
         a = flops_tile / (st["ms_tile_tensor"] * 1e-3) / 1e12
         tpeak, tsrc = (peaks["bf16_tflops_sustained"], "MEASURED_PEAKS.json bf16_tflops_sustained (measured; fp16 and bf16 share the tensor pipe rate)") \
             if "bf16_tflops_sustained" in peaks else (1400.0, "fallback 1.4 PFLOP/s sustained")
@@ -305,7 +305,7 @@ def run_b200(args, rank, world, local_rank):
                      "note": "algorithmic = 200 flop per (query,row) pair (SURVEY 8d); the MMA issues K=112 (100 dims + 3 norm terms + pad) "
                              "on every pair-slot of a 256-query x 128-row tile"}
     rl_direct = None
-    if st["ms_direct"] > 0:
+    if st["n_direct"] > 0 and st["ms_direct"] > 0:
         b = 400.0 * st["pairs_direct"]                  # B_pair: 400 B per pair, no reuse
         a = b / (st["ms_direct"] * 1e-3) / 1e9
         rl_direct = {"kernel": "k_direct", "bound": "hbm", "achieved": a, "peak": hbm_peak, "unit": "GB/s", "frac": a / hbm_peak,

@@ -75,6 +75,8 @@ def test_seeded_vs_oracle(H, oracle, check, datagen, n, m, ncat, seed):
             assert st["n_tile"] == 0 and st["n_direct"] == m
         if mode == H.MODE_EXACT and n >= 50_000:
             assert st["n_tile"] > 0 and st["n_items_ffma"] > 0 and st["n_items_tensor"] == 0, st
+        if mode == H.MODE_AUTO and n >= 50_000:         # the tcgen05 sweep ran, and it is exact too
+            assert st["n_tile"] > 0 and st["n_items_tensor"] > 0 and st["n_items_ffma"] == 0, st
 
 
 def test_selective_type3_pad_heavy(H, oracle, check, datagen):
