@@ -315,10 +315,13 @@ def run_b200(args, rank, world, local_rank):
     roofline = by_kernel.get(dom[:2]) or rl_tensor or rl_ffma or rl_direct
     others = [r for r in (rl_ffma, rl_tensor, rl_direct) if r is not None and r is not roofline]
 
-    line = {"metric": "queries/sec", "value": world * m / (ms_step * 1e-3), "unit": "queries/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+    # query-sharded: every rank solves its own Q-sized batch (weak scaling); data-sharded: all ranks solve the SAME batch
+    total_q = m if data_sharded else world * m
+    line = {"metric": "queries/sec", "value": total_q / (ms_step * 1e-3), "unit": "queries/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong" if data_sharded else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(round(st["launches"] * args.steps)),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(round((st["launches"] + (1 if data_sharded else 0)) * args.steps)),
             "roofline": roofline, "roofline_other": others, "dominant_kernel": dom,
             "kernel_ms_per_step": kern,
             "stats": {k: st[k] for k in ("pairs", "pairs_tile", "pairs_direct", "pairs_computed", "n_direct", "n_tile",
@@ -327,7 +330,7 @@ def run_b200(args, rank, world, local_rank):
             "alg_tflops_whole_step": 200.0 * st["pairs"] / (ms_step * 1e-3) / 1e12}
 
     # ---- parity on a sample, outside the timed region (the oracle is the checker, never the thing measured)
-    if not args.no_parity and not data_sharded:
+    if not args.no_parity and not data_sharded and world == 1:
         from oracle import check, oracle as O
         pick = np.linspace(0, m - 1, 8).astype(np.int64)
         t0 = time.perf_counter()
@@ -340,7 +343,7 @@ def run_b200(args, rank, world, local_rank):
         p = check.compare(d, q[pick], ref, ids_dev[pick], rtol=1e-4 if "optimized" in who else 1e-5)
         line["parity"] = {"against": who, "queries": int(len(pick)), "ok": bool(p.ok), "recall_at_100": p.recall_mean,
                           "max_rel_dist_err": p.max_rel, "secs": time.perf_counter() - t0}
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         qs, _ = sample_queries(q, args.cpu_sample)
         best, allv = cpu_reference_run(d, qs, 1, 0)
         line["cpu_baseline"] = {"value": qs.shape[0] / best["secs"], "unit": "queries/s", "cores": best["threads"],
