@@ -68,7 +68,7 @@ k_finalize(const float *__restrict__ queries, const QSlice *__restrict__ slices,
     // phase 2: the reference's arithmetic on the survivors
     const int c1 = (int)S.p1.cnt;
     for (int i = tid; i < c1; i += FT) {
-        const uint32_t row = (uint32_t)S.p1.cand[i] & 0x7fffffffu;   // K3 uses the top bit of the row word as a flag
+        const uint32_t row = (uint32_t)S.p1.cand[i];
         const float d = ref_dist_row(A.x + (size_t)row * DIM, S.q);
         S.p2.cand[i] = pack_key(d, row);
     }

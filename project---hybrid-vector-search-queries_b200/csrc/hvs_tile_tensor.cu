@@ -28,6 +28,7 @@
 //
 // Roofline: tensor pipe -- 2 x 7 MMAs (M128 N128 K16) = 896 tensor cycles per 128-row stage per SM;
 // the B stream is 28,672 B per stage per SM, read mostly from L2 (CTAs of one wave share the rows).
+#include <cstdio>
 #include <cstdlib>
 
 #include <cuda_fp16.h>
@@ -50,11 +51,8 @@ constexpr int STAGE_B = TN * ROW_B;   // 28,672
 constexpr int A_B = 128 * ROW_B;      // one query half
 constexpr int NTHR = 320;
 constexpr int POOL = TENSOR_POOL;     // survivor pool entries per query (global memory)
-constexpr int PER = POOL / 32;        // pool entries per lane when a warp sorts it
 constexpr uint32_t FULL = 0xffffffffu;
-constexpr int GB = TENSOR_GBEST;      // per-query list of the best scores seen by ANY CTA (global memory)
-constexpr uint32_t ROW_MASK = 0x7fffffffu, CONTRIB = 0x80000000u;   // top bit of a key's row word: "score already in gbest"
-constexpr uint32_t NOKEY = 0xffffffffu;
+constexpr int GB = TENSOR_GBEST;      // per-query global list of best scores over all finished chunks
 
 static_assert(QT_TENSOR == 256, "two M=128 halves");
 static_assert(POOL == 512 && KOUT <= POOL - 32, "pool must take 32 more survivors after a compaction");
@@ -122,193 +120,209 @@ struct QState {
     uint32_t cnt, qlo, qhi, qid;
 };
 
-// Warp-cooperative: merge up to 32 scores (one per lane, NOKEY for none; distinct rows) into the query's
-// global best-score list under the query's lock.  Returns the key of the list's K-th entry afterwards.
-// This is what makes thresholds tight everywhere: the K-th best score over ALL rows any CTA has seen
-// for this query bounds the final K-th best, whichever chunk of the slice a CTA is sweeping.
-__device__ __noinline__ uint32_t contribute32(uint32_t *__restrict__ gbest_q, uint32_t *__restrict__ lock_q, uint32_t newkey, int lane)
+// Pools are transposed: entry i of the query owned by lane l lives at pool_warp[i * 32 + l], so that the
+// 32 lanes of a warp walk their 32 pools in lock step with fully coalesced loads.
+//
+// Lane-parallel compaction: every lane that holds at least K survivors searches, privately, for a score v
+// with  K <= #{entries <= v} <= K + 8  (any v with at least K entries at or below it bounds the final K-th
+// best; the search is regula falsi on the counting function with a bisection step every third pass), then
+// rewrites its pool keeping only the entries within `margin` of v and tightens its threshold.
+// One call serves up to 32 queries; no sorting, no shuffles, a handful of coalesced passes over the pools.
+__device__ __noinline__ uint2 compact_warp(uint32_t cnt, float thr, float margin, uint32_t qid, bool valid,
+                                           uint64_t *__restrict__ pool_warp, uint32_t *__restrict__ gthr,
+                                           uint32_t *__restrict__ flags, uint32_t keep_cap, int lane)
 {
-    uint32_t key = newkey;
+    const bool part = valid && cnt >= (uint32_t)K;                    // lanes that take part
+    const uint32_t maxc = __reduce_max_sync(FULL, part ? cnt : 0u);
+    if (maxc == 0) return make_uint2(cnt, __float_as_uint(thr));
+    const uint32_t *sc = reinterpret_cast<const uint32_t *>(pool_warp) + 2 * lane + 1;   // score word of entry i: sc[64 i]
+    uint32_t klo = 0xffffffffu, khi = 0u;                             // range of the scores
+    for (uint32_t i0 = 0; i0 < maxc; i0 += 32) {                      // 32 independent loads in flight per lane
+        uint32_t k[32];
 #pragma unroll
-    for (int k = 2; k <= 32; k <<= 1)
+        for (int j = 0; j < 32; ++j) k[j] = __ldcg(sc + (size_t)64 * (i0 + j));
 #pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            const uint32_t other = __shfl_xor_sync(FULL, key, j);
-            const bool take_min = ((lane & j) == 0) == ((lane & k) == 0);
-            key = take_min ? min(key, other) : max(key, other);
-        }
-    const uint32_t nb = __popc(__ballot_sync(FULL, key != NOKEY));
-    if (lane == 0) {
-        while (atomicCAS(lock_q, 0u, 1u) != 0u) __nanosleep(64);
-        __threadfence();
+        for (int j = 0; j < 32; ++j)
+            if (part && i0 + j < cnt) { klo = min(klo, k[j]); khi = max(khi, k[j]); }
     }
-    __syncwarp();
-    uint32_t g[GB / 32], cl[GB / 32];
-#pragma unroll
-    for (int j = 0; j < GB / 32; ++j) { g[j] = ld_relaxed_u32(gbest_q + lane + 32 * j); cl[j] = 0; }
-    uint32_t myrank = 0;
-    for (uint32_t t = 0; t < nb; ++t) {
-        const uint32_t nk = __shfl_sync(FULL, key, t);
+    // invariant: #{<= klo} = clo < K <= chi = #{<= khi}
+    bool done = !part || klo == khi;
+    uint32_t clo = 0, chi = cnt;
+    if (!done) klo -= 1;
+    for (int it = 0; it < 40 && !__all_sync(FULL, done); ++it) {
+        uint32_t mid;
+        if (it % 3 == 2) mid = klo + ((khi - klo) >> 1);
+        else {
+            const unsigned long long num = (unsigned long long)(khi - klo) * (uint32_t)(K + 4 - clo);
+            mid = klo + (uint32_t)(num / max(chi - clo, 1u));
+        }
+        mid = min(max(mid, klo + 1u), khi - 1u);
         uint32_t c = 0;
+        for (uint32_t i0 = 0; i0 < maxc; i0 += 32) {
+            uint32_t k[32];
 #pragma unroll
-        for (int j = 0; j < GB / 32; ++j) {
-            const bool le = g[j] <= nk;       // equal scores: the list entry goes first
-            c += le;
-            cl[j] += !le;
+            for (int j = 0; j < 32; ++j) k[j] = __ldcg(sc + (size_t)64 * (i0 + j));
+#pragma unroll
+            for (int j = 0; j < 32; ++j) c += (i0 + j < cnt && k[j] <= mid) ? 1u : 0u;
         }
-        c = __reduce_add_sync(FULL, c);
-        if ((uint32_t)lane == t) myrank = c;
-    }
-    __syncwarp();
-    uint32_t kth = 0;
-#pragma unroll
-    for (int j = 0; j < GB / 32; ++j) {
-        const uint32_t pos = lane + 32 * j + cl[j];
-        if (pos < (uint32_t)GB) {
-            if (cl[j]) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(gbest_q + pos), "r"(g[j]) : "memory");
-            if (pos == (uint32_t)(K - 1)) kth = g[j];
+        if (!done) {
+            if (c >= (uint32_t)K) { khi = mid; chi = c; done = c <= (uint32_t)K + 8u; }
+            else { klo = mid; clo = c; }
+            if (khi - klo <= 1u) done = true;
         }
     }
-    if ((uint32_t)lane < nb) {
-        const uint32_t pos = lane + myrank;
-        if (pos < (uint32_t)GB) {
-            asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(gbest_q + pos), "r"(key) : "memory");
-            if (pos == (uint32_t)(K - 1)) kth = key;
-        }
-    }
-    kth = __reduce_max_sync(FULL, kth);
-    __threadfence();
-    __syncwarp();
-    if (lane == 0) atomicExch(lock_q, 0u);
-    return kth;
-}
-
-// Warp-cooperative: sort lane `l`'s pool in registers (bitonic over 32 lanes x PER registers,
-// element e = j*32 + lane), keep what is within the margin of the K-th best, hand the best scores that
-// are news to the query's global list, tighten thresholds.
-struct CompactOut { uint32_t cnt; float thr; };
-__device__ __noinline__ CompactOut compact_lane(int l, uint32_t my_cnt, float my_thr, float my_margin, uint32_t my_qid,
-                                                uint64_t *__restrict__ pool_warp, uint32_t *__restrict__ gthr,
-                                                uint32_t *__restrict__ gbest, uint32_t *__restrict__ glock,
-                                                uint32_t *__restrict__ flags, int lane)
-{
-    const uint32_t n = __shfl_sync(FULL, my_cnt, l);
-    const float margin = __shfl_sync(FULL, my_margin, l);
-    const uint32_t qid = __shfl_sync(FULL, my_qid, l);
-    uint64_t *P = pool_warp + (size_t)l * POOL;
-    uint64_t k[PER];
-#pragma unroll
-    for (int j = 0; j < PER; ++j) {
-        const uint32_t e = j * 32 + lane;
-        k[j] = e < n ? P[e] : KEY_INF;
-    }
-#pragma unroll
-    for (int size = 2; size <= POOL; size <<= 1) {
-#pragma unroll
-        for (int d = size >> 1; d > 0; d >>= 1) {
-            if (d >= 32) {                                   // partner is another register of this lane
-                const int dj = d >> 5;
-#pragma unroll
-                for (int j = 0; j < PER; ++j) {
-                    if ((j & dj) == 0) {
-                        const bool up = (((j * 32) & size) == 0);   // lane bits are below `size` here (size >= 64)
-                        const uint64_t a = k[j], b = k[j | dj];
-                        const bool sw = (a > b) == up;
-                        k[j] = sw ? b : a;
-                        k[j | dj] = sw ? a : b;
-                    }
-                }
-            } else {                                         // partner is the same register of lane ^ d
-#pragma unroll
-                for (int j = 0; j < PER; ++j) {
-                    const uint64_t o = __shfl_xor_sync(FULL, k[j], d);
-                    const uint32_t e = j * 32 + lane;
-                    const bool up = (e & size) == 0;
-                    const bool lower = (lane & d) == 0;
-                    const bool take_min = lower == up;
-                    k[j] = take_min ? (k[j] < o ? k[j] : o) : (k[j] < o ? o : k[j]);
-                }
-            }
-        }
-    }
-    // sorted ascending by e = j*32 + lane
-    uint32_t keep = n;
+    // keep what is within the margin of that bound
     float lim = __int_as_float(0x7f800000);
-    bool ovf = false;
-    if (n >= (uint32_t)K) {
-        const uint64_t kk = __shfl_sync(FULL, k[(K - 1) >> 5], (K - 1) & 31);
-        lim = okey_inv((uint32_t)(kk >> 32)) + margin;
-        uint32_t nin = 0;
+    uint32_t limk = 0xffffffffu;
+    if (part) { lim = okey_inv(khi) + margin; limk = okey(lim); }
+    uint32_t w = 0;
+    for (uint32_t i0 = 0; i0 < maxc; i0 += 16) {
+        uint64_t e[16];
 #pragma unroll
-        for (int j = 0; j < PER; ++j)
-            if ((uint32_t)(j * 32 + lane) < n && okey_inv((uint32_t)(k[j] >> 32)) <= lim) ++nin;
-        keep = __reduce_add_sync(FULL, nin);
-        if (keep > (uint32_t)KOUT) { keep = KOUT; ovf = true; }   // more rows inside the margin than a list may hold
+        for (int j = 0; j < 16; ++j) e[j] = __ldcg(pool_warp + (size_t)32 * (i0 + j) + lane);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (part && i0 + j < cnt && (uint32_t)(e[j] >> 32) <= limk) { pool_warp[(size_t)32 * w + lane] = e[j]; ++w; }
     }
-    // the best GB entries that are not in the global list yet and would enter it
-    uint32_t *gbest_q = gbest + (size_t)qid * GB;
-    uint32_t gk = ld_relaxed_u32(gbest_q + GB - 1);               // worst score the global list still holds
-    uint32_t kth = ld_relaxed_u32(gbest_q + K - 1);
-#pragma unroll
-    for (int j = 0; j < GB / 32; ++j) {
-        const uint32_t sc = (uint32_t)(k[j] >> 32);
-        const bool want = (uint32_t)(j * 32 + lane) < keep && !((uint32_t)k[j] & CONTRIB) && sc < gk;
-        if (__any_sync(FULL, want)) {
-            kth = contribute32(gbest_q, glock + qid, want ? sc : NOKEY, lane);
-            if (want) k[j] |= (uint64_t)CONTRIB;
-            gk = ld_relaxed_u32(gbest_q + GB - 1);
+    if (part) {
+        if (w > keep_cap) {                                           // more rows inside the margin than a list may hold:
+            flags[qid] = 1u;                                          // K4 re-solves this query exactly
+            w = keep_cap;
         }
+        cnt = w;
+        const float mine = nextafterf(lim, __int_as_float(0x7f800000));
+        const float theirs = okey_inv(ld_relaxed_u32(&gthr[qid]));
+        if (mine < theirs) atomicMin(&gthr[qid], okey(mine));
+        thr = fminf(thr, fminf(mine, theirs));
     }
     __syncwarp();
-#pragma unroll
-    for (int j = 0; j < PER; ++j) {
-        const uint32_t e = j * 32 + lane;
-        if (e < keep) P[e] = k[j];
-    }
-    CompactOut out{my_cnt, my_thr};
-    if (lane == l) {
-        out.cnt = keep;
-        if (ovf) flags[my_qid] = 1u;                          // K4 re-solves this query exactly
-        const float glim = okey_inv(kth) + margin;            // +inf while the global list holds fewer than K scores
-        const float mine = nextafterf(fminf(lim, glim), __int_as_float(0x7f800000));
-        const float theirs = okey_inv(ld_relaxed_u32(&gthr[my_qid]));
-        if (mine < theirs) atomicMin(&gthr[my_qid], okey(mine));
-        out.thr = fminf(my_thr, fminf(mine, theirs));
-    }
-    __syncwarp();
-    return out;
+    return make_uint2(cnt, __float_as_uint(thr));
 }
 
-// Warp-cooperative, item end: tell the query's global list about pool entries it has not seen (no sort).
-// Returns the (possibly tightened) threshold for lane `l`.
-__device__ __noinline__ float contribute_pool(int l, uint32_t my_cnt, float my_thr, float my_margin, uint32_t my_qid,
-                                              uint64_t *__restrict__ pool_warp, uint32_t *__restrict__ gthr,
-                                              uint32_t *__restrict__ gbest, uint32_t *__restrict__ glock, int lane)
+// Lane-parallel, item end: every lane folds the scores of its pool (the survivors of THIS row chunk) into
+// its query's global list of best scores -- at most GB scores of distinct rows, any order, guarded by a
+// per-query try-lock -- and derives a threshold from the K-th best score over ALL chunks finished so far.
+// This is what lets a CTA that sweeps one chunk of a slice filter with (nearly) the final threshold.
+// Chunks are disjoint and every item contributes exactly once, so no row is ever counted twice.
+// gcnt[q] = number of scores in the list, gcut[q] = key of its K-th best (0xffffffff while it holds < K).
+__device__ __noinline__ float merge_global(uint32_t cnt, float thr, float margin, uint32_t qid, bool valid,
+                                           const uint64_t *__restrict__ pool_warp, uint32_t *__restrict__ gbest,
+                                           uint32_t *__restrict__ gcnt, uint32_t *__restrict__ gcut,
+                                           uint32_t *__restrict__ glock, uint32_t *__restrict__ gthr, int lane)
 {
-    const uint32_t n = __shfl_sync(FULL, my_cnt, l);
-    const float margin = __shfl_sync(FULL, my_margin, l);
-    const uint32_t qid = __shfl_sync(FULL, my_qid, l);
-    uint64_t *P = pool_warp + (size_t)l * POOL;
-    uint32_t *gbest_q = gbest + (size_t)qid * GB;
-    uint32_t gk = ld_relaxed_u32(gbest_q + GB - 1);
-    uint32_t kth = NOKEY;
-    for (uint32_t base = 0; base < n; base += 32) {
-        const uint32_t e = base + lane;
-        const uint64_t kk = e < n ? P[e] : KEY_INF;
-        const uint32_t sc = (uint32_t)(kk >> 32);
-        const bool want = e < n && !((uint32_t)kk & CONTRIB) && sc < gk;
-        if (__any_sync(FULL, want)) {
-            kth = contribute32(gbest_q, glock + qid, want ? sc : NOKEY, lane);
-            if (want) P[e] = kk | (uint64_t)CONTRIB;
-            gk = ld_relaxed_u32(gbest_q + GB - 1);
+    const uint32_t *sc = reinterpret_cast<const uint32_t *>(pool_warp) + 2 * lane + 1;   // score word of pool entry i: sc[64 i]
+    bool want = valid && cnt > 0;
+    // nothing to tell if no survivor of this chunk beats the list's current K-th best
+    {
+        const uint32_t cutk = want ? ld_relaxed_u32(&gcut[qid]) : 0u;
+        const uint32_t maxc0 = __reduce_max_sync(FULL, want ? cnt : 0u);
+        bool better = false;
+        for (uint32_t i0 = 0; i0 < maxc0; i0 += 32) {
+            uint32_t k[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) k[j] = __ldcg(sc + (size_t)64 * (i0 + j));
+#pragma unroll
+            for (int j = 0; j < 32; ++j) better |= (i0 + j < cnt && k[j] < cutk);
+        }
+        want = want && better;
+    }
+    // Try-lock only: a lane that cannot get its query's lock skips the merge (the list only sharpens
+    // thresholds, it never decides results).  Blocking here could deadlock: the lanes of a warp hold 32
+    // different locks at once and reconverge before releasing them.
+    bool part = false;
+    for (int attempt = 0; attempt < 4 && __any_sync(FULL, want && !part); ++attempt) {
+        if (want && !part) part = atomicCAS(&glock[qid], 0u, 1u) == 0u;
+        if (attempt) __nanosleep(64);
+    }
+    if (!__any_sync(FULL, part)) return thr;
+    uint32_t *G = gbest + (size_t)qid * GB;
+    uint32_t gn = 0;
+    if (part) {
+        __threadfence();
+        gn = ld_relaxed_u32(&gcnt[qid]);
+    }
+    const uint32_t maxc = __reduce_max_sync(FULL, part ? cnt : 0u);
+    const uint32_t maxg = __reduce_max_sync(FULL, gn);                 // <= GB
+    const bool sel = part && gn + cnt >= (uint32_t)K;
+    uint32_t klo = 0xffffffffu, khi = 0u;
+    for (uint32_t i0 = 0; i0 < maxg; i0 += 16) {
+        uint32_t k[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) k[j] = (i0 + j < gn) ? __ldcg(G + i0 + j) : 0u;
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (i0 + j < gn) { klo = min(klo, k[j]); khi = max(khi, k[j]); }
+    }
+    for (uint32_t i0 = 0; i0 < maxc; i0 += 32) {
+        uint32_t k[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) k[j] = __ldcg(sc + (size_t)64 * (i0 + j));
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (part && i0 + j < cnt) { klo = min(klo, k[j]); khi = max(khi, k[j]); }
+    }
+    bool done = !sel || klo == khi;
+    uint32_t clo = 0, chi = gn + cnt;
+    if (!done) klo -= 1;
+    for (int it = 0; it < 40 && !__all_sync(FULL, done); ++it) {
+        uint32_t mid;
+        if (it % 3 == 2) mid = klo + ((khi - klo) >> 1);
+        else {
+            const unsigned long long num = (unsigned long long)(khi - klo) * (uint32_t)(K + 4 - clo);
+            mid = klo + (uint32_t)(num / max(chi - clo, 1u));
+        }
+        mid = min(max(mid, klo + 1u), khi - 1u);
+        uint32_t c = 0;
+        for (uint32_t i0 = 0; i0 < maxg; i0 += 16) {
+            uint32_t k[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) k[j] = (i0 + j < gn) ? __ldcg(G + i0 + j) : 0xffffffffu;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) c += (i0 + j < gn && k[j] <= mid) ? 1u : 0u;
+        }
+        for (uint32_t i0 = 0; i0 < maxc; i0 += 32) {
+            uint32_t k[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) k[j] = __ldcg(sc + (size_t)64 * (i0 + j));
+#pragma unroll
+            for (int j = 0; j < 32; ++j) c += (i0 + j < cnt && k[j] <= mid) ? 1u : 0u;
+        }
+        if (!done) {
+            if (c >= (uint32_t)K) { khi = mid; chi = c; done = c <= (uint32_t)K + 8u; }
+            else { klo = mid; clo = c; }
+            if (khi - klo <= 1u) done = true;
         }
     }
-    float thr = my_thr;
-    if (lane == l && kth != NOKEY) {
-        const float mine = nextafterf(okey_inv(kth) + margin, __int_as_float(0x7f800000));
-        const float theirs = okey_inv(ld_relaxed_u32(&gthr[my_qid]));
-        if (mine < theirs) atomicMin(&gthr[my_qid], okey(mine));
-        thr = fminf(my_thr, fminf(mine, theirs));
+    // new global list: with a bound, the scores at or below it (at most GB of them); without, everything
+    const uint32_t cut = sel ? khi : 0xffffffffu;
+    uint32_t w = 0;
+    for (uint32_t i0 = 0; i0 < maxg; i0 += 16) {                       // read a batch, then write: w never overtakes i0
+        uint32_t k[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) k[j] = (i0 + j < gn) ? __ldcg(G + i0 + j) : 0xffffffffu;
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (i0 + j < gn && k[j] <= cut) { G[w] = k[j]; ++w; }
+    }
+    for (uint32_t i0 = 0; i0 < maxc; i0 += 32) {
+        uint32_t k[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) k[j] = __ldcg(sc + (size_t)64 * (i0 + j));
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (part && i0 + j < cnt && k[j] <= cut && w < (uint32_t)GB) { G[w] = k[j]; ++w; }
+    }
+    if (part) {
+        gcnt[qid] = w;
+        if (sel) gcut[qid] = khi;
+        __threadfence();
+        atomicExch(&glock[qid], 0u);
+        if (sel) {
+            const float mine = nextafterf(okey_inv(khi) + margin, __int_as_float(0x7f800000));
+            const float theirs = okey_inv(ld_relaxed_u32(&gthr[qid]));
+            if (mine < theirs) atomicMin(&gthr[qid], okey(mine));
+            thr = fminf(thr, fminf(mine, theirs));
+        }
     }
     __syncwarp();
     return thr;
@@ -370,7 +384,8 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
               uint32_t n_items, const uint32_t *__restrict__ item_q, const unsigned char *__restrict__ img0,
               const unsigned char *__restrict__ img1, float xnorm_max, float sx, uint64_t *__restrict__ pool,
               uint64_t *__restrict__ cand, uint32_t *__restrict__ cand_cnt, uint32_t *__restrict__ gthr,
-              uint32_t *__restrict__ gbest, uint32_t *__restrict__ glock, uint32_t *__restrict__ flags, int dbg)
+              uint32_t *__restrict__ gbest, uint32_t *__restrict__ gcnt, uint32_t *__restrict__ gcut,
+              uint32_t *__restrict__ glock, uint32_t *__restrict__ flags, int dbg, unsigned long long *__restrict__ kstat)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TensorSmem &S = *reinterpret_cast<TensorSmem *>(smem_raw);
@@ -391,6 +406,10 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
     tc_fence_after();
     const uint32_t tmem = S.tmem_base;
 
+    long long c_mergeonly = 0, c_abuild = 0;
+    long long c_wait = 0, c_scan = 0, c_compact = 0, c_merge = 0, c_mma_full = 0, c_mma_tempty = 0, c_items = 0;
+    unsigned n_compact = 0, n_surv = 0;
+    const long long c_start = clock64();
     // running counters: the mbarrier phases continue across items
     uint32_t gt = 0;           // stages issued / consumed so far (producer, MMA)
     uint32_t ga[2] = {0, 0};   // accumulator uses so far, per half (MMA, epilogue)
@@ -402,6 +421,7 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
         const uint32_t row0 = it.row_begin & ~7u;                     // stages start on an 8-row group
         const uint32_t ntiles = (it.row_end - row0 + TN - 1) / TN;
 
+        const long long ta0 = clock64();
         // A operand: fp16(-2 sx q) | 1 1 1 | 0, written straight into the canonical layout.  All MMAs of the
         // previous item have retired (its epilogue consumed every accumulator before the barrier below).
         for (int idx = tid; idx < QT_TENSOR * KU; idx += NTHR) {
@@ -429,6 +449,7 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
         }
         fence_proxy_async();                                          // generic-proxy writes -> visible to the tensor core
         __syncthreads();
+        c_abuild += clock64() - ta0;
 
         if (warp == 0) {
             // ===== TMA producer (whole warp runs the loop, one elected lane talks to the TMA engine) =====
@@ -451,14 +472,14 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
             for (uint32_t t = 0; t < ntiles; ++t) {
                 const uint32_t g = gt + t;
                 const int st = g % NST;
-                mbar_wait(&S.full[st], (g / NST) & 1);
+                { const long long t0 = clock64(); mbar_wait(&S.full[st], (g / NST) & 1); c_mma_full += clock64() - t0; }
                 const uint64_t bdesc = smem_desc(smem_u32(S.b[st]));
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     if (h < nhalf) {
                         const uint32_t u = ga[h] + t;
                         const int b = u & 1;
-                        mbar_wait(&S.tempty[h][b], ((u >> 1) & 1) ^ 1);  // epilogue drained this accumulator
+                        { const long long t0 = clock64(); mbar_wait(&S.tempty[h][b], ((u >> 1) & 1) ^ 1); c_mma_tempty += clock64() - t0; }
                         tc_fence_after();
                         if (elect_one()) {
                             const uint32_t d = tmem + (uint32_t)(h * 2 + b) * TN;
@@ -481,7 +502,7 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
                 const uint32_t qslot0 = (uint32_t)(h * 128 + quad * 32);
                 const uint32_t qslot = qslot0 + lane;
                 uint64_t *pool_warp = pool + ((size_t)blockIdx.x * QT_TENSOR + qslot0) * POOL;
-                uint64_t *mypool = pool_warp + (size_t)lane * POOL;
+                uint64_t *mypool = pool_warp + lane;                     // entry i at mypool[32 i]
                 QState st;
                 st.cnt = 0; st.qid = 0; st.qlo = 1; st.qhi = 0; st.margin = 0.f;
                 st.thr = __int_as_float(0xff800000);                     // unused slot: nothing passes
@@ -495,6 +516,8 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
                     // -2 sx q must be representable in fp16: otherwise this query cannot use the tensor path
                     if (!(2.f * sx * sqrtf(sl.qnorm) < 60000.f)) { st.thr = __int_as_float(0xff800000); flags[st.qid] = 1u; }
                 }
+                if (dbg == 4 && qslot < it.nq) st.thr = 0.f;        // measurement only: (almost) nothing survives
+                if (dbg == 5 && qslot < it.nq) st.thr = 3550.f;     // measurement only: steady-state-like survival rate ~1e-4
                 const uint32_t tlane = tmem + ((uint32_t)(quad * 32) << 16);
                 // 32 columns (data rows) at a time: four 8-wide minima, one compare; only a group whose minimum
                 // beats the threshold is looked at element by element
@@ -517,28 +540,32 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
                                     const float s = __uint_as_float(r[c]);
                                     const uint32_t row = rbase + c;
                                     if (s < st.thr && row >= st.qlo && row < st.qhi)
-                                        mypool[st.cnt++] = ((uint64_t)okey(s) << 32) | row;
+                                        mypool[(size_t)32 * st.cnt++] = ((uint64_t)okey(s) << 32) | row;
                                 }
                             }
                     }
                 };
-                // room for 32 more survivors in every pool of this warp (else: sort, keep, tighten)
+                // room for 32 more survivors in every pool of this warp; when one pool is nearly full (or a query has
+                // no threshold yet) all 32 queries of the warp are compacted together
                 auto make_room = [&]() {
-                    uint32_t need = __ballot_sync(FULL, st.cnt > (uint32_t)(POOL - 32) ||
-                                                            (st.cnt >= 128u && st.thr == __int_as_float(0x7f800000)));
-                    while (need) {
-                        const int l = __ffs(need) - 1;
-                        need &= need - 1;
-                        const CompactOut o = compact_lane(l, st.cnt, st.thr, st.margin, st.qid, pool_warp, gthr, gbest, glock, flags, lane);
-                        st.cnt = o.cnt; st.thr = o.thr;
+                    if (dbg >= 3) { if (st.cnt > (uint32_t)(POOL - 32)) st.cnt = 0; return; }   // measurement only
+                    if (__any_sync(FULL, st.cnt > (uint32_t)(POOL - 32) ||
+                                             (st.cnt >= 192u && st.thr == __int_as_float(0x7f800000)))) {
+                        const long long t0 = clock64();
+                        n_surv += st.cnt;
+                        const uint2 o = compact_warp(st.cnt, st.thr, st.margin, st.qid, qslot < it.nq, pool_warp, gthr, flags, KOUT, lane);
+                        st.cnt = o.x; st.thr = __uint_as_float(o.y);
+                        n_surv -= st.cnt;
+                        c_compact += clock64() - t0; ++n_compact;
                     }
                 };
                 for (uint32_t t = 0; t < ntiles; ++t) {
                     const uint32_t u = ga[h] + t;
                     // a look at what other CTAs found out about this query
-                    if ((t & 7) == 7 && qslot < it.nq) st.thr = fminf(st.thr, okey_inv(ld_relaxed_u32(&gthr[st.qid])));
+                    if ((t & 7) == 7 && qslot < it.nq && dbg < 3) st.thr = fminf(st.thr, okey_inv(ld_relaxed_u32(&gthr[st.qid])));
                     const int b = u & 1;
-                    mbar_wait(&S.tfull[h][b], (u >> 1) & 1);
+                    { const long long t0 = clock64(); mbar_wait(&S.tfull[h][b], (u >> 1) & 1); c_wait += clock64() - t0; }
+                    const long long ts0 = clock64();
                     tc_fence_after();
                     const uint32_t tcol = tlane + (uint32_t)(h * 2 + b) * TN;
                     const uint32_t trow0 = row0 + t * TN;
@@ -581,47 +608,59 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&S.tempty[h][b]);
+                    c_scan += clock64() - ts0;
                 }
-                // hand the pool to K5: lists need not be sorted, only short enough
-                uint32_t need = __ballot_sync(FULL, st.cnt > (uint32_t)KOUT);
-                while (need) {
-                    const int l = __ffs(need) - 1;
-                    need &= need - 1;
-                    const CompactOut o = compact_lane(l, st.cnt, st.thr, st.margin, st.qid, pool_warp, gthr, gbest, glock, flags, lane);
-                    st.cnt = o.cnt; st.thr = o.thr;
+                // hand the pools to K5: lists need not be sorted, only short enough
+                if (__any_sync(FULL, st.cnt > (uint32_t)KOUT)) {
+                    const uint2 o = compact_warp(st.cnt, st.thr, st.margin, st.qid, qslot < it.nq, pool_warp, gthr, flags, KOUT, lane);
+                    st.cnt = o.x; st.thr = __uint_as_float(o.y);
                 }
-                // pools that hold scores the global list has not seen pass them on, so that the next items of
-                // these queries (other row chunks) start with tight thresholds
-                bool news = false;
-                if (st.cnt) {
-                    const uint32_t gk = ld_relaxed_u32(gbest + (size_t)st.qid * GB + GB - 1);
-                    for (uint32_t e = 0; e < st.cnt && !news; ++e) {
-                        const uint64_t kk = mypool[e];
-                        news = !((uint32_t)kk & CONTRIB) && (uint32_t)(kk >> 32) < gk;
+                // tell the other chunks of these queries what this chunk found (worth it only for long sweeps)
+                const long long tm0 = clock64();
+                n_surv += st.cnt;
+                if (ntiles >= 128u && dbg == 0)
+                    st.thr = merge_global(st.cnt, st.thr, st.margin, st.qid, qslot < it.nq, pool_warp, gbest, gcnt, gcut, glock, gthr, lane);
+                c_mergeonly += clock64() - tm0;
+                {
+                    const uint32_t maxc = __reduce_max_sync(FULL, st.cnt);
+                    uint64_t *L = cand + (size_t)(it.out_off + qslot) * KOUT;
+                    for (uint32_t i0 = 0; i0 < maxc; i0 += 16) {      // batches of 16 loads in flight
+                        uint64_t e[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) e[j] = __ldcg(mypool + (size_t)32 * (i0 + j));
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (i0 + j < st.cnt) L[i0 + j] = e[j];
                     }
                 }
-                need = __ballot_sync(FULL, news);
-                while (need) {
-                    const int l = __ffs(need) - 1;
-                    need &= need - 1;
-                    st.thr = contribute_pool(l, st.cnt, st.thr, st.margin, st.qid, pool_warp, gthr, gbest, glock, lane);
-                }
-                for (int l = 0; l < 32; ++l) {
-                    const uint32_t c = __shfl_sync(FULL, st.cnt, l);
-                    if (qslot0 + l >= it.nq) break;
-                    uint64_t *L = cand + (size_t)(it.out_off + qslot0 + l) * KOUT;
-                    const uint64_t *P = pool_warp + (size_t)l * POOL;
-                    for (uint32_t e = lane; e < c; e += 32) L[e] = P[e];
-                }
                 if (qslot < it.nq) cand_cnt[it.out_off + qslot] = st.cnt;
+                c_merge += clock64() - tm0;
             }
         }
+        { const long long t0 = clock64();
         gt += ntiles;
         ga[0] += ntiles;
         if (nhalf == 2) ga[1] += ntiles;
         tc_fence_before();
         __syncthreads();                                              // item boundary: A may be rebuilt
         tc_fence_after();
+        c_items += clock64() - t0; }
+    }
+    if (kstat) {
+        const long long c_total = clock64() - c_start;
+        if (warp >= 2) {
+            n_surv = __reduce_add_sync(FULL, n_surv);
+            if (lane == 0) {
+                atomicAdd(&kstat[0], (unsigned long long)c_total); atomicAdd(&kstat[1], (unsigned long long)c_wait);
+                atomicAdd(&kstat[2], (unsigned long long)c_scan); atomicAdd(&kstat[3], (unsigned long long)c_compact);
+                atomicAdd(&kstat[4], (unsigned long long)c_merge); atomicAdd(&kstat[5], (unsigned long long)c_items);
+                atomicAdd(&kstat[6], (unsigned long long)n_compact); atomicAdd(&kstat[7], (unsigned long long)n_surv);
+                atomicAdd(&kstat[8], 1ull); atomicAdd(&kstat[13], (unsigned long long)c_mergeonly); atomicAdd(&kstat[14], (unsigned long long)c_abuild);
+            }
+        } else if (warp == 1 && lane == 0) {
+            atomicAdd(&kstat[9], (unsigned long long)c_total); atomicAdd(&kstat[10], (unsigned long long)c_mma_full);
+            atomicAdd(&kstat[11], (unsigned long long)c_mma_tempty); atomicAdd(&kstat[12], 1ull);
+        }
     }
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
@@ -647,19 +686,37 @@ cudaError_t launch_tile_tensor(hvs_engine *e, const float *queries_dev, const QS
     if (c != cudaSuccess) return c;
     c = e->d_gbest.ensure((size_t)e->stats.m * GB * 4);
     if (c != cudaSuccess) return c;
-    c = e->d_glock.ensure((size_t)e->stats.m * 4);
+    c = e->d_glock.ensure((size_t)e->stats.m * 12);                                                  // [m] locks, [m] counts, [m] K-th keys
     if (c != cudaSuccess) return c;
-    c = launch_fill_u32(e, e->d_gbest.as<uint32_t>(), 0xff800000u /* okey(+inf) */, (size_t)e->stats.m * GB);
+    c = cudaMemsetAsync(e->d_glock.p, 0, (size_t)e->stats.m * 8, e->stream);
     if (c != cudaSuccess) return c;
-    c = cudaMemsetAsync(e->d_glock.p, 0, (size_t)e->stats.m * 4, e->stream);
+    c = cudaMemsetAsync(e->d_glock.as<uint32_t>() + 2 * (size_t)e->stats.m, 0xff, (size_t)e->stats.m * 4, e->stream);
     if (c != cudaSuccess) return c;
+    static const bool want_stats = getenv("HVS_K3_STATS") != nullptr;
+    unsigned long long *kstat = nullptr;
+    if (want_stats) {
+        c = e->d_scratch.ensure(256);
+        if (c != cudaSuccess) return c;
+        cudaMemsetAsync(e->d_scratch.p, 0, 256, e->stream);
+        kstat = e->d_scratch.as<unsigned long long>();
+    }
     static const bool pipe = [] { const char *v = getenv("HVS_K3_PIPE"); return v && v[0] == '1'; }();
     static const int dbg = [] { const char *v = getenv("HVS_K3_DBG"); return v ? atoi(v) : 0; }();
     auto kern = pipe ? k_tile_tensor<true> : k_tile_tensor<false>;
     kern<<<grid, NTHR, smem, e->stream>>>(queries_dev, slices_dev, items_dev + item_begin, n_items, item_q_dev,
                                           ix.xb[0].as<unsigned char>(), ix.xb[1].as<unsigned char>(), ix.xnorm_max, ix.img_scale,
                                           e->d_pool.as<uint64_t>(), cand_dev, cand_cnt_dev, gthr_dev, e->d_gbest.as<uint32_t>(),
-                                          e->d_glock.as<uint32_t>(), flags_dev, dbg);
+                                          e->d_glock.as<uint32_t>() + e->stats.m, e->d_glock.as<uint32_t>() + 2 * (size_t)e->stats.m,
+                                          e->d_glock.as<uint32_t>(), flags_dev, dbg, kstat);
+    if (kstat) {
+        unsigned long long h[16];
+        cudaStreamSynchronize(e->stream);
+        cudaMemcpy(h, kstat, sizeof h, cudaMemcpyDeviceToHost);
+        const double ew = (double)h[8], mw = (double)h[12];
+        fprintf(stderr, "K3 stats per epilogue warp (Mcycles): total %.2f  wait_tfull %.2f  scan %.2f  (of which compact %.2f, n=%.1f)  item_end %.2f (merge_global %.2f)  A-build %.2f  barrier %.2f | survivors/warp %.0f | MMA warp: total %.2f wait_full %.2f wait_tempty %.2f\n",
+                h[0] / ew / 1e6, h[1] / ew / 1e6, h[2] / ew / 1e6, h[3] / ew / 1e6, h[6] / ew, h[4] / ew / 1e6, h[13] / ew / 1e6, h[14] / ew / 1e6, h[5] / ew / 1e6, h[7] / ew,
+                h[9] / mw / 1e6, h[10] / mw / 1e6, h[11] / mw / 1e6);
+    }
     return cudaGetLastError();
 }
 
