@@ -49,7 +49,7 @@ constexpr int TN = 128;               // data rows per stage == MMA N
 constexpr int NST = 6;                // B stages in flight
 constexpr int STAGE_B = TN * ROW_B;   // 28,672
 constexpr int A_B = 128 * ROW_B;      // one query half
-constexpr int NTHR = 320;
+constexpr int NTHR = 352;              // warp 0 TMA, warp 1 MMA issuer of query half 0, warps 2..9 epilogue, warp 10 MMA issuer of half 1
 constexpr int POOL = TENSOR_POOL;     // survivor pool entries per query (global memory)
 constexpr uint32_t FULL = 0xffffffffu;
 constexpr int GB = TENSOR_GBEST;      // per-query global list of best scores over all finished chunks
@@ -236,12 +236,43 @@ __device__ __noinline__ float merge_global(uint32_t cnt, float thr, float margin
     }
     if (!__any_sync(FULL, part)) return thr;
     uint32_t *G = gbest + (size_t)qid * GB;
-    uint32_t gn = 0;
+    uint32_t gn = 0, cut_old = 0xffffffffu;
     if (part) {
         __threadfence();
         gn = ld_relaxed_u32(&gcnt[qid]);
+        cut_old = ld_relaxed_u32(&gcut[qid]);
     }
     const uint32_t maxc = __reduce_max_sync(FULL, part ? cnt : 0u);
+    // Cheap case: the survivors that beat the list's K-th best still fit into the list -> append them and keep
+    // the bound (it then stands for the (K + a few)-th best, which is still a valid, slightly lazier bound).
+    // Only when the list would overflow is a new K-th best selected.
+    uint32_t nbeat = 0;
+    for (uint32_t i0 = 0; i0 < maxc; i0 += 32) {
+        uint32_t k[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) k[j] = __ldcg(sc + (size_t)64 * (i0 + j));
+#pragma unroll
+        for (int j = 0; j < 32; ++j) nbeat += (part && i0 + j < cnt && k[j] < cut_old) ? 1u : 0u;
+    }
+    const bool need_sel = part && (gn + nbeat > (uint32_t)GB || (cut_old == 0xffffffffu && gn + nbeat >= (uint32_t)K));
+    if (!__any_sync(FULL, need_sel)) {
+        uint32_t w = gn;
+        for (uint32_t i0 = 0; i0 < maxc; i0 += 32) {
+            uint32_t k[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) k[j] = __ldcg(sc + (size_t)64 * (i0 + j));
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (part && i0 + j < cnt && k[j] < cut_old) { G[w] = k[j]; ++w; }
+        }
+        if (part) {
+            gcnt[qid] = w;
+            __threadfence();
+            atomicExch(&glock[qid], 0u);
+        }
+        __syncwarp();
+        return thr;
+    }
     const uint32_t maxg = __reduce_max_sync(FULL, gn);                 // <= GB
     const bool sel = part && gn + cnt >= (uint32_t)K;
     uint32_t klo = 0xffffffffu, khi = 0u;
@@ -392,7 +423,7 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
-        for (int s = 0; s < NST; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
+        for (int s = 0; s < NST; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 2); }   // both MMA issuers release a stage
         for (int h = 0; h < 2; ++h)
             for (int b = 0; b < 2; ++b) { mbar_init(&S.tfull[h][b], 1); mbar_init(&S.tempty[h][b], 4); }
         mbar_fence_init();
@@ -464,35 +495,34 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
                 }
                 __syncwarp();
             }
-        } else if (warp == 1) {
-            // ===== MMA issuer: warp-uniform control flow, one elected lane issues =====
-            // Accumulator (half h, buffer b) = TMEM columns [128 (2h+b), +128): the epilogue drains buffer b of
-            // a half while the tensor core fills buffer b^1 with the next stage.
-            const uint64_t adesc0 = smem_desc(smem_u32(S.a[0])), adesc1 = smem_desc(smem_u32(S.a[1]));
+        } else if (warp == 1 || warp == 10) {
+            // ===== MMA issuers: one warp per query half, warp-uniform control flow, one elected lane issues =====
+            // Accumulator (half h, buffer b) = TMEM columns [128 (2h+b), +128): the epilogue drains buffer b of a
+            // half while the tensor core fills buffer b^1 with the next stage.  The two halves are independent
+            // pipelines (own issuer, own barriers): a slow epilogue warp in one half never delays the other.
+            const int h = warp == 1 ? 0 : 1;
+            const uint64_t adesc = smem_desc(smem_u32(S.a[h]));
             for (uint32_t t = 0; t < ntiles; ++t) {
                 const uint32_t g = gt + t;
                 const int st = g % NST;
                 { const long long t0 = clock64(); mbar_wait(&S.full[st], (g / NST) & 1); c_mma_full += clock64() - t0; }
-                const uint64_t bdesc = smem_desc(smem_u32(S.b[st]));
+                tc_fence_after();
+                if (h < nhalf) {
+                    const uint64_t bdesc = smem_desc(smem_u32(S.b[st]));
+                    const uint32_t u = ga[h] + t;
+                    const int b = u & 1;
+                    { const long long t0 = clock64(); mbar_wait(&S.tempty[h][b], ((u >> 1) & 1) ^ 1); c_mma_tempty += clock64() - t0; }
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t d = tmem + (uint32_t)(h * 2 + b) * TN;
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    if (h < nhalf) {
-                        const uint32_t u = ga[h] + t;
-                        const int b = u & 1;
-                        { const long long t0 = clock64(); mbar_wait(&S.tempty[h][b], ((u >> 1) & 1) ^ 1); c_mma_tempty += clock64() - t0; }
-                        tc_fence_after();
-                        if (elect_one()) {
-                            const uint32_t d = tmem + (uint32_t)(h * 2 + b) * TN;
-                            const uint64_t ad = h ? adesc1 : adesc0;
-#pragma unroll
-                            for (int j = 0; j < KP / 16; ++j)            // one k-step = two 16-byte units = 256 bytes
-                                tc_mma(d, ad + (uint64_t)(j * 16), bdesc + (uint64_t)(j * 16), IDESC, j > 0);
-                            tc_commit(&S.tfull[h][b]);
-                        }
-                        __syncwarp();
+                        for (int j = 0; j < KP / 16; ++j)                // one k-step = two 16-byte units = 256 bytes
+                            tc_mma(d, adesc + (uint64_t)(j * 16), bdesc + (uint64_t)(j * 16), IDESC, j > 0);
+                        tc_commit(&S.tfull[h][b]);
                     }
+                    __syncwarp();
                 }
-                if (elect_one()) tc_commit(&S.empty[st]);               // stage may be refilled once these MMAs retire
+                if (elect_one()) tc_commit(&S.empty[st]);               // this half is done with the stage once its MMAs retire
                 __syncwarp();
             }
         } else {
@@ -648,7 +678,7 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
     }
     if (kstat) {
         const long long c_total = clock64() - c_start;
-        if (warp >= 2) {
+        if (warp >= 2 && warp < 10) {
             n_surv = __reduce_add_sync(FULL, n_surv);
             if (lane == 0) {
                 atomicAdd(&kstat[0], (unsigned long long)c_total); atomicAdd(&kstat[1], (unsigned long long)c_wait);
@@ -657,7 +687,7 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
                 atomicAdd(&kstat[6], (unsigned long long)n_compact); atomicAdd(&kstat[7], (unsigned long long)n_surv);
                 atomicAdd(&kstat[8], 1ull); atomicAdd(&kstat[13], (unsigned long long)c_mergeonly); atomicAdd(&kstat[14], (unsigned long long)c_abuild);
             }
-        } else if (warp == 1 && lane == 0) {
+        } else if ((warp == 1 || warp == 10) && lane == 0) {
             atomicAdd(&kstat[9], (unsigned long long)c_total); atomicAdd(&kstat[10], (unsigned long long)c_mma_full);
             atomicAdd(&kstat[11], (unsigned long long)c_mma_tempty); atomicAdd(&kstat[12], 1ull);
         }
