@@ -85,6 +85,7 @@ extern "C" int hvs_create(hvs_engine **out, const hvs_config *cfg)
         e->own_stream = true;
     }
     for (auto &ev : e->ev) cudaEventCreate(&ev);
+    for (auto &ev : e->evg) cudaEventCreate(&ev);
     e->stats.struct_size = sizeof(hvs_stats);
     *out = e;
     return HVS_OK;
@@ -104,6 +105,7 @@ extern "C" void hvs_destroy(hvs_engine *e)
     for (DevBuf *b : bufs) b->release();
     e->h_slices.release(); e->h_stage.release();
     for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : e->evg) if (ev) cudaEventDestroy(ev);
     if (e->own_stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -179,37 +181,28 @@ static int solve_impl(hvs_engine *e, const float *q_dev, uint32_t m, bool partia
     pp.mode = e->mode;
     pp.tensor_available = tensor_path_available() && e->index.xb[0].p != nullptr;
     Plan &P = e->plan;
-    plan_build(e->h_slices.as<QSlice>(), m, pp, P);
+    const QSlice *h_sl = e->h_slices.as<QSlice>();
+    plan_begin(h_sl, m, pp, P);                      // classify; tile queries are cut into groups of chunk blocks
     st.pairs = P.pairs;
-    st.pairs_computed = P.pairs_computed;
     st.pairs_tile = P.pairs_tile;
     st.pairs_direct = P.pairs - P.pairs_tile;
     st.n_direct = (uint32_t)P.direct_q.size();
-    st.n_tile = (uint32_t)P.tile_q.size();
-    st.n_items_ffma = P.n_ffma;
-    st.n_items_tensor = P.n_tensor;
 
-    // upload work lists (one staging buffer, one copy per list)
-    const size_t b_direct = P.direct_q.size() * 4, b_items = P.items.size() * sizeof(TileItem), b_itemq = P.item_q.size() * 4,
-                 b_tileq = P.tile_q.size() * 4, b_qoff = P.q_list_off.size() * 4, b_ql = P.q_lists.size() * 4;
-    ECUDA(e->h_stage.ensure(b_direct + b_items + b_itemq + b_tileq + b_qoff + b_ql + 64));
+    // one pinned staging buffer for all uploads of this solve; every upload gets its own region
+    const size_t n_groups = P.group_end.size();
+    const size_t max_items = (size_t)(P.incid / (P.BQ ? P.BQ : 1)) + 2 * (P.R ? ((size_t)e->index.n / P.R + 2) : 0) + 64;
+    ECUDA(e->h_stage.ensure(P.direct_q.size() * 4 + max_items * sizeof(TileItem) + (size_t)P.incid * 8 + (size_t)m * 12 + 1024));
     unsigned char *hs = e->h_stage.as<unsigned char>();
     size_t o = 0;
-    auto up = [&](DevBuf &db, const void *src, size_t bytes) -> cudaError_t {
+    auto up_at = [&](void *dst, const void *src, size_t bytes) -> cudaError_t {
         if (!bytes) return cudaSuccess;
-        cudaError_t c = db.ensure(bytes);
-        if (c != cudaSuccess) return c;
         std::memcpy(hs + o, src, bytes);
-        c = cudaMemcpyAsync(db.p, hs + o, bytes, cudaMemcpyHostToDevice, s);
+        cudaError_t c = cudaMemcpyAsync(dst, hs + o, bytes, cudaMemcpyHostToDevice, s);
         o += (bytes + 15) & ~(size_t)15;
         return c;
     };
-    ECUDA(up(e->d_direct_q, P.direct_q.data(), b_direct));
-    ECUDA(up(e->d_items, P.items.data(), b_items));
-    ECUDA(up(e->d_item_q, P.item_q.data(), b_itemq));
-    ECUDA(up(e->d_tile_q, P.tile_q.data(), b_tileq));
-    ECUDA(up(e->d_qoff, P.q_list_off.data(), b_qoff));
-    ECUDA(up(e->d_qlists, P.q_lists.data(), b_ql));
+    ECUDA(e->d_direct_q.ensure(P.direct_q.size() * 4 + 16));
+    ECUDA(up_at(e->d_direct_q.p, P.direct_q.data(), P.direct_q.size() * 4));
     cudaEventRecord(e->ev[3], s);
 
     // K4: direct scans
@@ -219,29 +212,51 @@ static int solve_impl(hvs_engine *e, const float *q_dev, uint32_t m, bool partia
     }
     cudaEventRecord(e->ev[4], s);
 
-    // K2 / K3: tile sweeps, then K5
-    if (!P.items.empty()) {
-        ECUDA(e->d_cand.ensure((size_t)P.n_lists * KOUT * 8));
-        ECUDA(e->d_cand_cnt.ensure((size_t)P.n_lists * 4));
+    // K2 / K3: tile sweeps, group by group -- the GPU sweeps group g while the host plans group g + 1 -- then K5
+    bool any_items = false;
+    bool ran[8] = {false, false, false, false, false, false, false, false};
+    if (P.incid) {
+        any_items = true;
+        ECUDA(e->d_items.ensure(max_items * sizeof(TileItem)));
+        ECUDA(e->d_item_q.ensure((size_t)P.incid * 4));
+        ECUDA(e->d_cand.ensure((size_t)P.incid * KOUT * 8));
+        ECUDA(e->d_cand_cnt.ensure((size_t)P.incid * 4));
         ECUDA(e->d_flags.ensure((size_t)m * 4));
         ECUDA(cudaMemsetAsync(e->d_flags.p, 0, (size_t)m * 4, s));
         ECUDA(e->d_gthr.ensure((size_t)m * 4));
         ECUDA(launch_fill_u32(e, e->d_gthr.as<uint32_t>(), 0xff800000u /* okey(+inf) */, m));
-        const TileItem *d_items = e->d_items.as<TileItem>();
-        cudaEventRecord(e->ev[5], s);
-        if (P.n_ffma && P.n_tensor) EFAIL(HVS_ERR_STATE, "planner mixed FFMA and tensor items in one solve");
-        if (P.n_ffma) {
-            ECUDA(launch_tile_ffma(e, q_dev, d_sl, d_items, 0, P.n_ffma, e->d_item_q.as<uint32_t>(), e->d_cand.as<uint64_t>(),
-                                   e->d_cand_cnt.as<uint32_t>(), e->d_gthr.as<uint32_t>(), e->d_flags.as<uint32_t>(), 1.0f));
+        st.launches++;
+        if (P.tensor) ECUDA(tile_tensor_begin(e));
+        TileItem *d_items = e->d_items.as<TileItem>();
+        for (size_t g = 0; g < n_groups; ++g) {
+            uint32_t ib = 0, ie = 0;
+            const size_t iq0 = P.item_q.size();
+            plan_group(h_sl, P, g, ib, ie);
+            if (ie == ib) continue;
+            if (ie > max_items) EFAIL(HVS_ERR_STATE, "planner produced more items than it announced");
+            ECUDA(up_at(d_items + ib, P.items.data() + ib, (size_t)(ie - ib) * sizeof(TileItem)));
+            ECUDA(up_at(e->d_item_q.as<uint32_t>() + iq0, P.item_q.data() + iq0, (P.item_q.size() - iq0) * 4));
+            if (g < 8) cudaEventRecord(e->evg[2 * g], s);
+            if (P.tensor)
+                ECUDA(launch_tile_tensor(e, q_dev, d_sl, d_items, ib, ie - ib, e->d_item_q.as<uint32_t>(), e->d_cand.as<uint64_t>(),
+                                         e->d_cand_cnt.as<uint32_t>(), e->d_gthr.as<uint32_t>(), e->d_flags.as<uint32_t>()));
+            else
+                ECUDA(launch_tile_ffma(e, q_dev, d_sl, d_items, ib, ie - ib, e->d_item_q.as<uint32_t>(), e->d_cand.as<uint64_t>(),
+                                       e->d_cand_cnt.as<uint32_t>(), e->d_gthr.as<uint32_t>(), e->d_flags.as<uint32_t>(), 1.0f));
+            if (g < 8) { cudaEventRecord(e->evg[2 * g + 1], s); ran[g] = true; }
             st.launches++;
         }
-        cudaEventRecord(e->ev[6], s);
-        if (P.n_tensor) {
-            ECUDA(launch_tile_tensor(e, q_dev, d_sl, d_items, 0, P.n_tensor, e->d_item_q.as<uint32_t>(),
-                                     e->d_cand.as<uint64_t>(), e->d_cand_cnt.as<uint32_t>(), e->d_gthr.as<uint32_t>(),
-                                     e->d_flags.as<uint32_t>()));
-            st.launches++;
-        }
+        plan_finish(h_sl, m, P);                     // candidate-list CSR, built while the last group is swept
+        st.pairs_computed = P.pairs_computed;
+        st.n_tile = (uint32_t)P.tile_q.size();
+        st.n_items_ffma = P.n_ffma;
+        st.n_items_tensor = P.n_tensor;
+        ECUDA(e->d_tile_q.ensure(P.tile_q.size() * 4 + 16));
+        ECUDA(e->d_qoff.ensure(P.q_list_off.size() * 4 + 16));
+        ECUDA(e->d_qlists.ensure(P.q_lists.size() * 4 + 16));
+        ECUDA(up_at(e->d_tile_q.p, P.tile_q.data(), P.tile_q.size() * 4));
+        ECUDA(up_at(e->d_qoff.p, P.q_list_off.data(), P.q_list_off.size() * 4));
+        ECUDA(up_at(e->d_qlists.p, P.q_lists.data(), P.q_lists.size() * 4));
         cudaEventRecord(e->ev[7], s);
         ECUDA(launch_finalize(e, q_dev, d_sl, e->d_tile_q.as<uint32_t>(), (uint32_t)P.tile_q.size(), e->d_qoff.as<uint32_t>(),
                               e->d_qlists.as<uint32_t>(), e->d_cand.as<uint64_t>(), e->d_cand_cnt.as<uint32_t>(),
@@ -266,12 +281,13 @@ static int solve_impl(hvs_engine *e, const float *q_dev, uint32_t m, bool partia
     cudaEventRecord(e->ev[9], s);
     ECUDA(cudaStreamSynchronize(s));
     ECUDA(cudaGetLastError());
-    st.ms_plan = ev_ms(e->ev[2], e->ev[3]);
+    st.ms_plan = ev_ms(e->ev[2], e->ev[3]);          // slice search + classification; group planning overlaps the sweeps
     st.ms_direct = ev_ms(e->ev[3], e->ev[4]);
-    if (!P.items.empty()) {
-        st.ms_tile_ffma = ev_ms(e->ev[5], e->ev[6]);
-        st.ms_tile_tensor = ev_ms(e->ev[6], e->ev[7]);
-        st.ms_tile = st.ms_tile_ffma + st.ms_tile_tensor;
+    if (any_items) {
+        float tile = 0.f;
+        for (size_t g = 0; g < n_groups && g < 8; ++g) if (ran[g]) tile += ev_ms(e->evg[2 * g], e->evg[2 * g + 1]);
+        if (P.tensor) st.ms_tile_tensor = tile; else st.ms_tile_ffma = tile;
+        st.ms_tile = tile;
         st.ms_finalize = ev_ms(e->ev[7], e->ev[8]);
     }
     st.ms_solve_device = ev_ms(e->ev[2], e->ev[9]);

@@ -104,11 +104,21 @@ struct Plan {
     std::vector<uint64_t> sort_keys[2];
     std::vector<uint32_t> order[2], nlist, qpos;
     std::vector<uint8_t> is_tile;
+    // incremental planning (plan_begin / plan_group / plan_finish): the sweep of group g runs on the GPU while
+    // the host builds group g + 1
+    struct Task { uint32_t arena, c0, c1; uint64_t incid; };
+    std::vector<Task> tasks;
+    std::vector<uint32_t> group_end;      // tasks [group_end[g-1], group_end[g]) form group g
+    uint32_t R = 0, BQ = 0;
+    bool tensor = false;
+    uint64_t incid = 0;                   // (chunk, query) incidences == candidate lists of the whole solve
+    unsigned nthreads = 1;
     void reset()
     {
         direct_q.clear(); items.clear(); item_q.clear(); tile_q.clear(); q_list_off.clear(); q_lists.clear();
         pairs = pairs_computed = pairs_tile = 0;
         n_lists = n_ffma = n_tensor = 0;
+        tasks.clear(); group_end.clear(); incid = 0; R = 0;
     }
 };
 
@@ -121,7 +131,10 @@ struct PlanParams {
     bool tensor_available = false;
 };
 
-void plan_build(const QSlice *slices, uint32_t m, const PlanParams &pp, Plan &out);
+void plan_build(const QSlice *slices, uint32_t m, const PlanParams &pp, Plan &out);     // begin + every group + finish
+void plan_begin(const QSlice *slices, uint32_t m, const PlanParams &pp, Plan &out);     // classify, order, cut into groups
+void plan_group(const QSlice *slices, Plan &out, size_t g, uint32_t &item_begin, uint32_t &item_end);   // items of one group
+void plan_finish(const QSlice *slices, uint32_t m, Plan &out);                          // candidate-list CSR per query
 
 }  // namespace hvs
 
@@ -140,6 +153,7 @@ struct hvs_engine {
     hvs::DevBuf d_cand, d_cand_cnt, d_scratch, d_flags, d_gthr, d_pool, d_gbest, d_glock, d_work_counter, d_rescore_ids, d_rescore_out;
     hvs::HostPinned h_slices, h_stage;
     cudaEvent_t ev[12]{};
+    cudaEvent_t evg[16]{};     // start/end of each group's tile launch
     hvs::Plan plan;
 };
 
@@ -161,6 +175,7 @@ cudaError_t launch_tile_tensor(hvs_engine *e, const float *queries_dev, const QS
                                const TileItem *items_dev, uint32_t item_begin, uint32_t n_items,
                                const uint32_t *item_q_dev, uint64_t *cand_dev, uint32_t *cand_cnt_dev,
                                uint32_t *gthr_dev, uint32_t *flags_dev);
+cudaError_t tile_tensor_begin(hvs_engine *e);
 cudaError_t launch_fill_u32(hvs_engine *e, uint32_t *dst, uint32_t value, size_t n);
 cudaError_t launch_finalize(hvs_engine *e, const float *queries_dev, const QSlice *slices_dev,
                             const uint32_t *tile_q_dev, uint32_t n_tile_q, const uint32_t *qoff_dev,

@@ -100,7 +100,21 @@ cudaError_t launch_plan_search(hvs_engine *e, const float *queries_dev, uint32_t
 //
 // Everything is counting sorts over (chunk, query) incidences -- O(m log m + incidences), no
 // comparator sorts over the incidence list.
-void plan_build(const QSlice *sl, uint32_t m, const PlanParams &pp, Plan &P)
+namespace {
+template <class F>
+void plan_parallel(unsigned nthreads, size_t njobs, F &&job)
+{
+    if (nthreads <= 1 || njobs <= 1) { for (size_t j = 0; j < njobs; ++j) job(j); return; }
+    std::atomic<size_t> next{0};
+    auto worker = [&]() { for (size_t j; (j = next.fetch_add(1)) < njobs;) job(j); };
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < nthreads && t < njobs; ++t) th.emplace_back(worker);
+    worker();
+    for (auto &t : th) t.join();
+}
+}  // namespace
+
+void plan_begin(const QSlice *sl, uint32_t m, const PlanParams &pp, Plan &P)
 {
     static const bool dbg = getenv("HVS_PLAN_DEBUG") != nullptr;
     auto T0 = std::chrono::steady_clock::now();
@@ -154,6 +168,8 @@ void plan_build(const QSlice *sl, uint32_t m, const PlanParams &pp, Plan &P)
         return x < y;
     });
     lap("classify");
+    P.tensor = tensor;
+    P.BQ = BQ;
     if (!tile_qrows) return;
 
     // chunk size: aim at ~16 items per SM over the whole job, power of two
@@ -162,23 +178,11 @@ void plan_build(const QSlice *sl, uint32_t m, const PlanParams &pp, Plan &P)
     uint32_t R = 8192;
     while ((uint64_t)R * 2 <= want) R *= 2;
     if (R > (1u << 22)) R = 1u << 22;
+    P.R = R;
 
-    // ---- (chunk, query) incidences -> items.  Independent per (arena, block of chunks): host threads.
-    struct Task { uint32_t arena, c0, c1; };
-    using Local = Plan::Local;
     std::vector<uint32_t> *order = P.order;
-    std::vector<Task> tasks;
     uint64_t incid = 0;
-    unsigned nthreads = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 8u);
-    auto parallel = [&](size_t njobs, auto &&job) {
-        if (nthreads <= 1 || njobs <= 1) { for (size_t j = 0; j < njobs; ++j) job(j); return; }
-        std::atomic<size_t> next{0};
-        auto worker = [&]() { for (size_t j; (j = next.fetch_add(1)) < njobs;) job(j); };
-        std::vector<std::thread> th;
-        for (unsigned t = 1; t < nthreads && t < njobs; ++t) th.emplace_back(worker);
-        worker();
-        for (auto &t : th) t.join();
-    };
+    P.nthreads = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 8u);
     uint32_t maxend[2] = {0, 0};
     for (uint32_t a = 0; a < 2; ++a) { order[a].clear(); P.sort_keys[a].clear(); }
     for (uint32_t i = 0; i < m; ++i)
@@ -188,10 +192,11 @@ void plan_build(const QSlice *sl, uint32_t m, const PlanParams &pp, Plan &P)
             maxend[a] = std::max(maxend[a], sl[i].end);
             incid += (sl[i].end - 1) / R - sl[i].begin / R + 1;
         }
-    if (incid < 65536) nthreads = 1;
+    P.incid = incid;
+    if (incid < 65536) P.nthreads = 1;
     // tile queries of each arena ordered by (begin, end, index): each chunk's batches then group queries
     // with similar slices, which keeps the union of rows an item sweeps tight
-    parallel(2, [&](size_t a) {
+    plan_parallel(P.nthreads, 2, [&](size_t a) {
         std::vector<uint32_t> &ord = order[a];
         if (ord.empty()) return;
         bool same = true;                                            // all slices equal (e.g. unfiltered queries): already ordered
@@ -204,16 +209,43 @@ void plan_build(const QSlice *sl, uint32_t m, const PlanParams &pp, Plan &P)
             return x < y;
         });
     });
-    for (uint32_t a = 0; a < 2; ++a) {
+    // tasks = (arena, block of chunks); the (C,T) arena first: its slices are short, so the GPU gets work early
+    for (int a = 1; a >= 0; --a) {
         if (order[a].empty()) continue;
         const uint32_t nchunk = (maxend[a] + R - 1) / R;
         const uint32_t per = std::max(1u, (nchunk + 7) / 8);
-        for (uint32_t c = 0; c < nchunk; c += per) tasks.push_back({a, c, std::min(nchunk, c + per)});
+        for (uint32_t c = 0; c < nchunk; c += per) P.tasks.push_back({(uint32_t)a, c, std::min(nchunk, c + per), 0});
     }
+    for (auto &tk : P.tasks)
+        for (uint32_t i : order[tk.arena]) {
+            const uint32_t lo = std::max(sl[i].begin / R, tk.c0), hi = std::min((sl[i].end - 1) / R + 1, tk.c1);
+            if (hi > lo) tk.incid += hi - lo;
+        }
+    // groups: ~20 % / 40 % / 40 % of the incidences, so that little planning stands before the first launch
+    const int ng = incid >= 200000 && P.tasks.size() >= 3 ? 3 : 1;
+    const double cutf[3] = {ng == 1 ? 1.0 : 0.2, 0.6, 1.0};
+    uint64_t run = 0;
+    int g = 0;
+    for (size_t ti = 0; ti < P.tasks.size(); ++ti) {
+        run += P.tasks[ti].incid;
+        if (g < ng - 1 && (double)run >= cutf[g] * (double)incid) { P.group_end.push_back((uint32_t)ti + 1); ++g; }
+    }
+    P.group_end.push_back((uint32_t)P.tasks.size());
+    if (P.locals.size() < P.tasks.size()) P.locals.resize(P.tasks.size());
+    lap("order");
+}
+
+void plan_group(const QSlice *sl, Plan &P, size_t g, uint32_t &item_begin, uint32_t &item_end)
+{
+    using Local = Plan::Local;
+    const uint32_t R = P.R, BQ = P.BQ;
+    const bool tensor = P.tensor;
+    std::vector<uint32_t> *order = P.order;
     std::vector<Local> &locals = P.locals;
-    if (locals.size() < tasks.size()) locals.resize(tasks.size());
-    auto run_task = [&](size_t ti) {
-        const Task tk = tasks[ti];
+    const size_t t0 = g ? P.group_end[g - 1] : 0, t1 = P.group_end[g];
+    auto run_task = [&](size_t tj) {
+        const size_t ti = t0 + tj;
+        const Plan::Task tk = P.tasks[ti];
         Local &L = locals[ti];
         L.items.clear(); L.item_q.clear(); L.pairs_computed = 0;
         const std::vector<uint32_t> &ord = order[tk.arena];
@@ -259,44 +291,45 @@ void plan_build(const QSlice *sl, uint32_t m, const PlanParams &pp, Plan &P)
             }
         }
     };
-    parallel(tasks.size(), run_task);
-    lap("incidences");
-    size_t n_items = 0, n_itemq = 0;
-    for (size_t ti = 0; ti < tasks.size(); ++ti) { n_items += locals[ti].items.size(); n_itemq += locals[ti].item_q.size(); }
-    P.items.reserve(n_items);
-    P.item_q.reserve(n_itemq);
-    for (size_t ti = 0; ti < tasks.size(); ++ti) {
+    plan_parallel(P.nthreads, t1 - t0, run_task);
+    item_begin = (uint32_t)P.items.size();
+    for (size_t ti = t0; ti < t1; ++ti) {
         Local &L = locals[ti];
         const uint32_t base = (uint32_t)P.item_q.size();
         for (auto it : L.items) { it.q_off += base; P.items.push_back(it); }
         P.item_q.insert(P.item_q.end(), L.item_q.begin(), L.item_q.end());
         P.pairs_computed += L.pairs_computed;
     }
-    lap("concat");
-    // longest first (LPT); equal-cost items stay in (arena,row) order so that CTAs running
+    item_end = (uint32_t)P.items.size();
+    // longest first (LPT) inside the group; equal-cost items stay in (arena,row) order so that CTAs running
     // concurrently share the same rows in L2
-    std::stable_sort(P.items.begin(), P.items.end(), [](const TileItem &x, const TileItem &y) {
+    std::stable_sort(P.items.begin() + item_begin, P.items.end(), [](const TileItem &x, const TileItem &y) {
         return (x.row_end - x.row_begin) > (y.row_end - y.row_begin);
     });
-    // candidate lists: item-major after sorting; CSR per tile query by counting (order inside a query is irrelevant)
-    std::vector<uint32_t> &nlist = P.nlist, &qpos = P.qpos;
-    nlist.assign(m, 0);
-    uint32_t off = 0;
-    for (auto &it : P.items) {
-        it.out_off = off;
-        off += it.nq;
+    for (uint32_t k = item_begin; k < item_end; ++k) {
+        TileItem &it = P.items[k];
+        it.out_off = P.n_lists;
+        P.n_lists += it.nq;
         if (it.kind) ++P.n_tensor; else ++P.n_ffma;
     }
-    P.n_lists = off;
+}
+
+void plan_finish(const QSlice *sl, uint32_t m, Plan &P)
+{
+    (void)sl;
+    if (P.items.empty()) return;
+    const std::vector<uint8_t> &is_tile = P.is_tile;
+    // candidate lists: CSR per tile query by counting (order inside a query is irrelevant)
+    std::vector<uint32_t> &nlist = P.nlist, &qpos = P.qpos;
+    nlist.assign(m, 0);
     // every thread owns a range of query indices and scans all (item, slot) pairs: no atomics, sequential reads
-    const size_t nrange = nthreads > 1 ? nthreads : 1;
+    const size_t nrange = P.nthreads > 1 ? P.nthreads : 1;
     auto qrange = [&](size_t r, uint32_t &q0, uint32_t &q1) { q0 = (uint32_t)((uint64_t)m * r / nrange); q1 = (uint32_t)((uint64_t)m * (r + 1) / nrange); };
-    parallel(nrange, [&](size_t r) {
+    plan_parallel(P.nthreads, nrange, [&](size_t r) {
         uint32_t q0, q1;
         qrange(r, q0, q1);
         for (uint32_t q : P.item_q) if (q >= q0 && q < q1) ++nlist[q];
     });
-    lap("nlist");
     qpos.assign(m, 0);
     P.q_list_off.push_back(0);
     for (uint32_t i = 0; i < m; ++i)
@@ -306,7 +339,7 @@ void plan_build(const QSlice *sl, uint32_t m, const PlanParams &pp, Plan &P)
             P.q_list_off.push_back(qpos[i] + nlist[i]);
         }
     P.q_lists.resize(P.q_list_off.back());
-    parallel(nrange, [&](size_t r) {
+    plan_parallel(P.nthreads, nrange, [&](size_t r) {
         uint32_t q0, q1;
         qrange(r, q0, q1);
         for (const TileItem &it : P.items) {
@@ -317,7 +350,16 @@ void plan_build(const QSlice *sl, uint32_t m, const PlanParams &pp, Plan &P)
             }
         }
     });
-    lap("q_lists");
+}
+
+void plan_build(const QSlice *sl, uint32_t m, const PlanParams &pp, Plan &P)
+{
+    plan_begin(sl, m, pp, P);
+    for (size_t g = 0; g < P.group_end.size(); ++g) {
+        uint32_t b, e;
+        plan_group(sl, P, g, b, e);
+    }
+    plan_finish(sl, m, P);
 }
 
 }  // namespace hvs

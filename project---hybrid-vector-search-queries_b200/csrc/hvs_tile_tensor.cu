@@ -697,6 +697,22 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
     }
 }
 
+// once per solve, before the first K3 launch: survivor pools and the per-query global lists
+cudaError_t tile_tensor_begin(hvs_engine *e)
+{
+    cudaError_t c = e->d_pool.ensure((size_t)e->sm_count * QT_TENSOR * POOL * 8);
+    if (c != cudaSuccess) return c;
+    c = e->d_gbest.ensure((size_t)e->stats.m * GB * 4);
+    if (c != cudaSuccess) return c;
+    c = e->d_glock.ensure((size_t)e->stats.m * 12);                                                  // [m] locks, [m] counts, [m] K-th keys
+    if (c != cudaSuccess) return c;
+    c = cudaMemsetAsync(e->d_glock.p, 0, (size_t)e->stats.m * 8, e->stream);
+    if (c != cudaSuccess) return c;
+    c = cudaMemsetAsync(e->d_glock.as<uint32_t>() + 2 * (size_t)e->stats.m, 0xff, (size_t)e->stats.m * 4, e->stream);
+    if (c != cudaSuccess) return c;
+    return cudaSuccess;
+}
+
 cudaError_t launch_tile_tensor(hvs_engine *e, const float *queries_dev, const QSlice *slices_dev, const TileItem *items_dev,
                                uint32_t item_begin, uint32_t n_items, const uint32_t *item_q_dev, uint64_t *cand_dev,
                                uint32_t *cand_cnt_dev, uint32_t *gthr_dev, uint32_t *flags_dev)
@@ -712,16 +728,7 @@ cudaError_t launch_tile_tensor(hvs_engine *e, const float *queries_dev, const QS
     }
     const Index &ix = e->index;
     const uint32_t grid = n_items < (uint32_t)e->sm_count ? n_items : (uint32_t)e->sm_count;
-    cudaError_t c = e->d_pool.ensure((size_t)e->sm_count * QT_TENSOR * POOL * 8);
-    if (c != cudaSuccess) return c;
-    c = e->d_gbest.ensure((size_t)e->stats.m * GB * 4);
-    if (c != cudaSuccess) return c;
-    c = e->d_glock.ensure((size_t)e->stats.m * 12);                                                  // [m] locks, [m] counts, [m] K-th keys
-    if (c != cudaSuccess) return c;
-    c = cudaMemsetAsync(e->d_glock.p, 0, (size_t)e->stats.m * 8, e->stream);
-    if (c != cudaSuccess) return c;
-    c = cudaMemsetAsync(e->d_glock.as<uint32_t>() + 2 * (size_t)e->stats.m, 0xff, (size_t)e->stats.m * 4, e->stream);
-    if (c != cudaSuccess) return c;
+    cudaError_t c = cudaSuccess;
     static const bool want_stats = getenv("HVS_K3_STATS") != nullptr;
     unsigned long long *kstat = nullptr;
     if (want_stats) {
