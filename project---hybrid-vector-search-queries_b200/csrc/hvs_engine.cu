@@ -5,6 +5,7 @@
 //   -> K4 direct scan (sparse slices)  +  K2/K3 tile sweeps (shared slices) -> K5 finalize -> D2H ids.
 // No CPU fallback anywhere: every distance and every selection runs in the CUDA kernels of this
 // library; the host only plans.
+#include <algorithm>
 #include <chrono>
 #include <cstring>
 #include <mutex>
@@ -86,6 +87,8 @@ extern "C" int hvs_create(hvs_engine **out, const hvs_config *cfg)
     }
     for (auto &ev : e->ev) cudaEventCreate(&ev);
     for (auto &ev : e->evg) cudaEventCreate(&ev);
+    for (auto &ev : e->ev_sync) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking);
     e->stats.struct_size = sizeof(hvs_stats);
     *out = e;
     return HVS_OK;
@@ -106,6 +109,8 @@ extern "C" void hvs_destroy(hvs_engine *e)
     e->h_slices.release(); e->h_stage.release();
     for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : e->evg) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : e->ev_sync) if (ev) cudaEventDestroy(ev);
+    if (e->stream2) cudaStreamDestroy(e->stream2);
     if (e->own_stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -213,7 +218,7 @@ static int solve_impl(hvs_engine *e, const float *q_dev, uint32_t m, bool partia
     cudaEventRecord(e->ev[4], s);
 
     // K2 / K3: tile sweeps, group by group -- the GPU sweeps group g while the host plans group g + 1 -- then K5
-    bool any_items = false;
+    bool any_items = false, side_lane_used = false;
     bool ran[8] = {false, false, false, false, false, false, false, false};
     if (P.incid) {
         any_items = true;
@@ -236,16 +241,31 @@ static int solve_impl(hvs_engine *e, const float *q_dev, uint32_t m, bool partia
             if (ie > max_items) EFAIL(HVS_ERR_STATE, "planner produced more items than it announced");
             ECUDA(up_at(d_items + ib, P.items.data() + ib, (size_t)(ie - ib) * sizeof(TileItem)));
             ECUDA(up_at(e->d_item_q.as<uint32_t>() + iq0, P.item_q.data() + iq0, (P.item_q.size() - iq0) * 4));
-            if (g < 8) cudaEventRecord(e->evg[2 * g], s);
+            // odd groups run on a second stream with their own survivor pools, so that the tail of one launch
+            // (CTAs running out of items) overlaps the head of the next
+            cudaStream_t sg = (g & 1) && e->stream2 ? e->stream2 : s;
+            if (sg != s) {
+                cudaEventRecord(e->ev_sync[0], s);                 // everything enqueued so far: setup + this group's uploads
+                ECUDA(cudaStreamWaitEvent(sg, e->ev_sync[0], 0));
+            }
+            e->pool_slot = (uint32_t)(g & 1);
+            cudaStream_t saved = e->stream;
+            e->stream = sg;
+            if (g < 8) cudaEventRecord(e->evg[2 * g], sg);
+            cudaError_t lc;
             if (P.tensor)
-                ECUDA(launch_tile_tensor(e, q_dev, d_sl, d_items, ib, ie - ib, e->d_item_q.as<uint32_t>(), e->d_cand.as<uint64_t>(),
-                                         e->d_cand_cnt.as<uint32_t>(), e->d_gthr.as<uint32_t>(), e->d_flags.as<uint32_t>()));
+                lc = launch_tile_tensor(e, q_dev, d_sl, d_items, ib, ie - ib, e->d_item_q.as<uint32_t>(), e->d_cand.as<uint64_t>(),
+                                        e->d_cand_cnt.as<uint32_t>(), e->d_gthr.as<uint32_t>(), e->d_flags.as<uint32_t>());
             else
-                ECUDA(launch_tile_ffma(e, q_dev, d_sl, d_items, ib, ie - ib, e->d_item_q.as<uint32_t>(), e->d_cand.as<uint64_t>(),
-                                       e->d_cand_cnt.as<uint32_t>(), e->d_gthr.as<uint32_t>(), e->d_flags.as<uint32_t>(), 1.0f));
-            if (g < 8) { cudaEventRecord(e->evg[2 * g + 1], s); ran[g] = true; }
+                lc = launch_tile_ffma(e, q_dev, d_sl, d_items, ib, ie - ib, e->d_item_q.as<uint32_t>(), e->d_cand.as<uint64_t>(),
+                                      e->d_cand_cnt.as<uint32_t>(), e->d_gthr.as<uint32_t>(), e->d_flags.as<uint32_t>(), 1.0f);
+            if (g < 8) { cudaEventRecord(e->evg[2 * g + 1], sg); ran[g] = true; }
+            e->stream = saved;
+            ECUDA(lc);
+            if (sg != s) { cudaEventRecord(e->ev_sync[1], sg); side_lane_used = true; }
             st.launches++;
         }
+        if (side_lane_used) ECUDA(cudaStreamWaitEvent(s, e->ev_sync[1], 0));   // K5 needs every group's lists
         plan_finish(h_sl, m, P);                     // candidate-list CSR, built while the last group is swept
         st.pairs_computed = P.pairs_computed;
         st.n_tile = (uint32_t)P.tile_q.size();
@@ -284,8 +304,14 @@ static int solve_impl(hvs_engine *e, const float *q_dev, uint32_t m, bool partia
     st.ms_plan = ev_ms(e->ev[2], e->ev[3]);          // slice search + classification; group planning overlaps the sweeps
     st.ms_direct = ev_ms(e->ev[3], e->ev[4]);
     if (any_items) {
+        // the groups' launches overlap (two lanes): the tile phase is the span from the first start to the last end
         float tile = 0.f;
-        for (size_t g = 0; g < n_groups && g < 8; ++g) if (ran[g]) tile += ev_ms(e->evg[2 * g], e->evg[2 * g + 1]);
+        int g0 = -1;
+        for (size_t g = 0; g < n_groups && g < 8; ++g)
+            if (ran[g]) {
+                if (g0 < 0) g0 = (int)g;
+                tile = std::max(tile, ev_ms(e->evg[2 * g0], e->evg[2 * g + 1]));
+            }
         if (P.tensor) st.ms_tile_tensor = tile; else st.ms_tile_ffma = tile;
         st.ms_tile = tile;
         st.ms_finalize = ev_ms(e->ev[7], e->ev[8]);

@@ -144,6 +144,9 @@ struct hvs_engine {
     uint32_t id_offset = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t stream2 = nullptr;   // second lane for tile launches: the tail of group g overlaps the head of group g + 1
+    cudaEvent_t ev_sync[4]{};
+    uint32_t pool_slot = 0;           // which half of the survivor pools the next K3 launch uses
     int sm_count = 148;
     std::string err;
     hvs::Index index;

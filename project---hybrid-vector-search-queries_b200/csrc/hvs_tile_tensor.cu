@@ -700,7 +700,7 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
 // once per solve, before the first K3 launch: survivor pools and the per-query global lists
 cudaError_t tile_tensor_begin(hvs_engine *e)
 {
-    cudaError_t c = e->d_pool.ensure((size_t)e->sm_count * QT_TENSOR * POOL * 8);
+    cudaError_t c = e->d_pool.ensure((size_t)2 * e->sm_count * QT_TENSOR * POOL * 8);   // two pool sets: launches on the two lanes overlap
     if (c != cudaSuccess) return c;
     c = e->d_gbest.ensure((size_t)e->stats.m * GB * 4);
     if (c != cudaSuccess) return c;
@@ -742,7 +742,7 @@ cudaError_t launch_tile_tensor(hvs_engine *e, const float *queries_dev, const QS
     auto kern = pipe ? k_tile_tensor<true> : k_tile_tensor<false>;
     kern<<<grid, NTHR, smem, e->stream>>>(queries_dev, slices_dev, items_dev + item_begin, n_items, item_q_dev,
                                           ix.xb[0].as<unsigned char>(), ix.xb[1].as<unsigned char>(), ix.xnorm_max, ix.img_scale,
-                                          e->d_pool.as<uint64_t>(), cand_dev, cand_cnt_dev, gthr_dev, e->d_gbest.as<uint32_t>(),
+                                          e->d_pool.as<uint64_t>() + (size_t)e->pool_slot * e->sm_count * QT_TENSOR * POOL, cand_dev, cand_cnt_dev, gthr_dev, e->d_gbest.as<uint32_t>(),
                                           e->d_glock.as<uint32_t>() + e->stats.m, e->d_glock.as<uint32_t>() + 2 * (size_t)e->stats.m,
                                           e->d_glock.as<uint32_t>(), flags_dev, dbg, kstat);
     if (kstat) {
