@@ -14,20 +14,26 @@
 //
 // Persistent kernel, one CTA per SM, work items taken round-robin.  An item = up to 256 queries
 // (two M=128 halves sharing every B stage) x a run of arena rows.  Warp roles: warp 0 TMA producer,
-// warp 1 MMA issuer (+ TMEM owner), warps 2..9 epilogue (warp w reads TMEM lanes 32*(w%4)..; one
-// thread = one query).  Four accumulators of 128 columns (2 halves x 2 buffers) use all 512 TMEM
-// columns, so the epilogue of tile t overlaps the MMAs of tile t+1.
+// warp 1 / warp 10 MMA issuers of query half 0 / 1 (independent pipelines; warp 1 owns TMEM),
+// warps 2..9 epilogue (warp w reads TMEM lanes 32*(w%4)..; one thread = one query).  Four
+// accumulators of 128 columns (2 halves x 2 buffers) use all 512 TMEM columns, so the epilogue of
+// tile t overlaps the MMAs of tile t+1.
 //
 // The result is NOT approximate: a row survives when its fp16 score is within `margin_tensor`
 // (hvs_margin.cuh: a rigorous bound on the rounding of both operands) of the running 100-th best,
 // and K5 re-ranks all survivors with the reference's fp32 arithmetic.  Survivors are appended to a
-// per-(CTA, query) pool in global memory (L2 resident) by the thread that owns the query; when a
-// pool fills, one warp sorts it in registers, keeps what is still inside the margin and tightens
-// the threshold.  Thresholds are shared between all CTAs working on the same query (`gthr`,
-// atomicMin), so a CTA that starts late starts with a tight threshold.
+// per-(CTA, query) pool in global memory (L2 resident, transposed so that the 32 lanes of a warp walk
+// their 32 pools with coalesced loads) by the thread that owns the query.  When a pool fills, all 32
+// queries of the warp are compacted together, lane-parallel: each lane searches (regula falsi on the
+// counting function) for a score with ~100 entries at or below it, keeps what is within the margin
+// of it and tightens its threshold -- no sorting.  At the end of an item every lane folds its pool
+// into its query's GLOBAL list of best scores (all row chunks, per-query try-lock), so a CTA that
+// later sweeps another chunk of the slice starts with (nearly) the final threshold (`gthr`).
 //
 // Roofline: tensor pipe -- 2 x 7 MMAs (M128 N128 K16) = 896 tensor cycles per 128-row stage per SM;
-// the B stream is 28,672 B per stage per SM, read mostly from L2 (CTAs of one wave share the rows).
+// the epilogue must read the 128 KB of fp32 accumulators of a stage out of TMEM (the measured limit
+// of this design: ~1000 cycles per stage per SM sub-partition pair); the B stream is 28,672 B per
+// stage per SM.  HVS_K3_STATS=1 prints the cycle budget per warp role.
 #include <cstdio>
 #include <cstdlib>
 
