@@ -161,12 +161,23 @@ void plan_begin(const QSlice *sl, uint32_t m, const PlanParams &pp, Plan &P)
     }
     for (uint32_t i = 0; i < m; ++i)
         if (!is_tile[i]) { P.direct_q.push_back(i); P.pairs_computed += sl[i].end - sl[i].begin; }
-    // direct queries: neighbours in an arena share L2 lines
-    std::sort(P.direct_q.begin(), P.direct_q.end(), [&](uint32_t x, uint32_t y) {
-        if (sl[x].arena != sl[y].arena) return sl[x].arena < sl[y].arena;
-        if (sl[x].begin != sl[y].begin) return sl[x].begin < sl[y].begin;
-        return x < y;
-    });
+    // direct queries: neighbours in an arena share L2 lines.  A counting sort on (arena, begin >> 12) is all the
+    // locality the scan needs and costs O(m) (a comparator sort of 4x10^4 slices took 3 ms of a 4 ms solve).
+    if (P.direct_q.size() > 1) {
+        constexpr uint32_t NB = 4096;                                    // buckets per arena
+        uint32_t maxb = 0, SH = 0;
+        for (uint32_t q : P.direct_q) maxb = std::max(maxb, sl[q].begin);
+        while ((maxb >> SH) >= NB) ++SH;
+        std::vector<uint32_t> &cnt = P.nlist;                            // scratch, re-assigned by plan_finish
+        cnt.assign(2 * NB + 1, 0);
+        auto bucket = [&](uint32_t q) { return sl[q].arena * NB + (sl[q].begin >> SH); };
+        for (uint32_t q : P.direct_q) ++cnt[bucket(q) + 1];
+        for (uint32_t b = 0; b < 2 * NB; ++b) cnt[b + 1] += cnt[b];
+        std::vector<uint32_t> &out = P.qpos;                             // scratch as well
+        out.resize(P.direct_q.size());
+        for (uint32_t q : P.direct_q) out[cnt[bucket(q)]++] = q;
+        P.direct_q.swap(out);
+    }
     lap("classify");
     P.tensor = tensor;
     P.BQ = BQ;

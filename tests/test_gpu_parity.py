@@ -217,3 +217,62 @@ def test_vec_query_operator_contract(H, oracle, check):
     assert len(out) == len(g["q"]) and all(len(r) == 100 for r in out)
     p = check.compare(g["d"], g["q"], g["ids_baseline"], np.asarray(out, np.uint32), rtol=RTOL)
     assert p.ok, p.summary()
+
+
+def test_engine_reuse_and_batch_shapes(H, oracle, check, datagen):
+    """One index, many solves (what the C++ shim does once, a server would do repeatedly): results must not
+    depend on what was solved before, on the batch size, or on the mode of an earlier engine."""
+    d = datagen.gen_data(150_000, 61, ncat=6)
+    qa = datagen.gen_queries(700, 62, ncat=6)
+    qb = datagen.gen_queries(33, 63, ncat=6, types=(2, 3))
+    ref_a = oracle.vec_query(d, qa[:64], want_dist=False)
+    ref_b = oracle.vec_query(d, qb, want_dist=False)
+    with H.Engine(mode=H.MODE_AUTO) as e:
+        e.index_build(d)
+        a1 = e.solve(qa)
+        b1 = e.solve(qb)
+        one = e.solve(qa[5:6])
+        a2 = e.solve(qa)
+        e.index_build(d[:100_000])                       # re-index the same engine with less data
+        small = e.solve(qb)
+        e.index_build(d)
+        a3 = e.solve(qa)
+    assert np.array_equal(a1, a2) and np.array_equal(a1, a3)
+    assert np.array_equal(one[0], a1[5])
+    p = check.compare(d, qa[:64], ref_a, a1[:64], rtol=RTOL)
+    assert p.ok and p.dist_bit_identical_rows == 64, p.summary()
+    p = check.compare(d, qb, ref_b, b1, rtol=RTOL)
+    assert p.ok and p.dist_bit_identical_rows == len(qb), p.summary()
+    ref_small = oracle.vec_query(d[:100_000], qb, want_dist=False)
+    p = check.compare(d[:100_000], qb, ref_small, small, rtol=RTOL)
+    assert p.ok, p.summary()
+
+
+def test_cpp_driver_same_files_same_bytes(H, oracle, check, datagen, tmp_path):
+    """The drop-in driver (reference command line and file formats, include/hvs_vec_query.hpp underneath):
+    output.bin must be M x 100 uint32 without header (include/io.h:23-36) and hold the reference's answer;
+    output.bin.dist is what src/compare_data.cpp reads."""
+    import os
+    import subprocess
+    drv = os.path.join(os.path.dirname(H.LIB_PATH), "driver", "hvs_test.out")
+    if not os.path.exists(drv):
+        pytest.skip("driver not built")
+    d = datagen.gen_data(20_000, 71, ncat=12)
+    q = datagen.gen_queries(120, 72, ncat=12)
+    dp, qp, op = str(tmp_path / "d.bin"), str(tmp_path / "q.bin"), str(tmp_path / "out.bin")
+    datagen.write_bin(dp, d)
+    datagen.write_bin(qp, q)
+    r = subprocess.run([drv, dp, qp, op], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "Vector Search took" in r.stderr
+    raw = np.fromfile(op, np.uint32)
+    assert raw.size == len(q) * 100                       # headerless
+    ids = raw.reshape(len(q), 100)
+    ref = oracle.vec_query(d, q, want_dist=False)
+    p = check.compare(d, q, ref, ids, rtol=RTOL)
+    assert p.ok and p.dist_bit_identical_rows == len(q), p.summary()
+    with open(op + ".dist", "rb") as f:
+        m = int(np.fromfile(f, np.uint32, 1)[0])
+        dist = np.fromfile(f, np.float32).reshape(m, 100)
+    assert m == len(q)
+    assert np.array_equal(dist.view(np.uint32), oracle.rescore(d, q, ids).view(np.uint32))
