@@ -137,6 +137,14 @@ def cpu_reference_run(d, q_sample, steps, warmup):
                 ts.append(time.perf_counter() - t0)
         out["port"] = {"kind": "port", "desc": "oracle/hvs_oracle.c restatement of baseline.hpp", "secs": float(np.mean(ts)), "threads": 1}
     best = min(out.values(), key=lambda v: v["secs"])
+    # the reference's oracle of record, baseline.hpp (IMPL=1, scalar, one thread), on one query per type
+    if O.ref_available("baseline") and q_sample.shape[0] >= 4:
+        t = q_sample[:, 0].astype(int)
+        pick = [int(np.nonzero(t == k)[0][0]) for k in sorted(set(t.tolist()))][:4]
+        qb = np.ascontiguousarray(q_sample[pick])
+        _, secs = O.ref_vec_query("baseline", d, qb)
+        out["baseline"] = {"kind": "reference", "desc": "baseline.hpp (IMPL=1), one thread", "secs": float(secs), "threads": 1,
+                           "queries": len(pick)}
     return best, out
 
 
@@ -163,7 +171,8 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": best["threads"], "kind": best["kind"],
                              "sample": f"{qs.shape[0]} of the workload's {m} queries (every {m // max(1, qs.shape[0])}-th, same type mix) "
                                        f"against the full D={n}; {best['desc']}; host has {os.cpu_count()} cores",
-                             "variants": {k: {"secs_per_step": v["secs"], "threads": v["threads"]} for k, v in allv.items()}},
+                             "variants": {k: {"queries_per_s": v.get("queries", qs.shape[0]) / v["secs"], "threads": v["threads"],
+                                              "what": v["desc"]} for k, v in allv.items()}},
             "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -196,10 +205,14 @@ def run_b200(args, rank, world, local_rank):
     if data_sharded:
         lo, hi = importlib.import_module(PKG + ".sharding").data_shard(n, rank, world)
         eng = hvs.Engine(device=local_rank, mode=mode, stream=stream.cuda_stream, id_offset=lo)
+        t_ix = time.perf_counter()
         eng.index_build(d[lo:hi])
+        t_ix = time.perf_counter() - t_ix
     else:
         eng = hvs.Engine(device=local_rank, mode=mode, stream=stream.cuda_stream)
+        t_ix = time.perf_counter()
         eng.index_build(d)
+        t_ix = time.perf_counter() - t_ix
     st_index = eng.stats()
 
     q_pinned = torch.from_numpy(q).pin_memory()
@@ -311,6 +324,15 @@ def run_b200(args, rank, world, local_rank):
         rl_direct = {"kernel": "k_direct", "bound": "hbm", "achieved": a, "peak": hbm_peak, "unit": "GB/s", "frac": a / hbm_peak,
                      "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({hbm_src})", "traffic": None,
                      "algorithmic_bytes_per_launch": b, "ms_per_launch": st["ms_direct"]}
+    # DRAM traffic per step of each kernel, from the committed ncu capture of this same workload (profiles/r1_traffic.json)
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(args.workload, {})
+    except (OSError, ValueError):
+        traffic = {}
+    for r in (rl_ffma, rl_tensor, rl_direct):
+        if r is not None and r["kernel"] in traffic:
+            r["traffic"] = traffic[r["kernel"]]["dram_bytes_per_step"]
+            r["traffic_source"] = traffic[r["kernel"]]["source"]
     by_kernel = {"K2": rl_ffma, "K3": rl_tensor, "K4": rl_direct}
     roofline = by_kernel.get(dom[:2]) or rl_tensor or rl_ffma or rl_direct
     others = [r for r in (rl_ffma, rl_tensor, rl_direct) if r is not None and r is not roofline]
@@ -327,6 +349,10 @@ def run_b200(args, rank, world, local_rank):
             "stats": {k: st[k] for k in ("pairs", "pairs_tile", "pairs_direct", "pairs_computed", "n_direct", "n_tile",
                                          "n_items_ffma", "n_items_tensor", "n_fallback", "launches", "ms_solve_device")},
             "index_build_ms": st_index["ms_index_build"],
+            "indexing_phase": {"host_to_index_wall_ms": t_ix * 1e3, "device_ms": st_index["ms_index_build"],
+                               "bytes_streamed": int(d.shape[0] if not data_sharded else hi - lo) * 408,
+                               "note": "hvs_index_build: pageable host rows -> pinned double buffer -> H2D -> radix sorts, gathers, fp16 "
+                                       "images; done once, never sees queries; not part of a step"},
             "alg_tflops_whole_step": 200.0 * st["pairs"] / (ms_step * 1e-3) / 1e12}
 
     # ---- parity on a sample, outside the timed region (the oracle is the checker, never the thing measured)
@@ -349,7 +375,9 @@ def run_b200(args, rank, world, local_rank):
         line["cpu_baseline"] = {"value": qs.shape[0] / best["secs"], "unit": "queries/s", "cores": best["threads"],
                                 "kind": best["kind"],
                                 "sample": f"{qs.shape[0]} of the {m} queries (every {m // max(1, qs.shape[0])}-th, same type mix) against the "
-                                          f"full D={n}, one pass; {best['desc']}; host has {os.cpu_count()} cores"}
+                                          f"full D={n}, one pass; {best['desc']}; host has {os.cpu_count()} cores",
+                                "variants": {k: {"queries_per_s": v.get("queries", qs.shape[0]) / v["secs"], "threads": v["threads"],
+                                                 "what": v["desc"]} for k, v in allv.items()}}
     print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:

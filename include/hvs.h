@@ -120,6 +120,16 @@ HVS_API void hvs_destroy(hvs_engine *e);
  */
 HVS_API int hvs_index_build(hvs_engine *e, const float *rows_host, uint32_t n, float sample_proportion);
 HVS_API int hvs_index_build_device(hvs_engine *e, const float *rows_dev, uint32_t n, float sample_proportion);
+/*
+ * The same from the layouts the reference's loader produces, without an intermediate copy.  D is streamed to the
+ * device through two pinned staging buffers filled by host threads while the previous chunk is in flight.
+ *   _rows      : n row pointers, each to 102 floats -- std::vector<std::vector<float>> as ReadBin builds it
+ *                (include/io.h:123-133: one heap block per row) and as vec_query receives it (src/test.cpp:85)
+ *   _from_file : the D file itself (uint32 N, then N x 102 float32; README.md:32-44, include/io.h:111-136),
+ *                read with pread into the pinned buffers; *out_n (may be NULL) receives N
+ */
+HVS_API int hvs_index_build_rows(hvs_engine *e, const float *const *row_ptrs, uint32_t n, float sample_proportion);
+HVS_API int hvs_index_build_from_file(hvs_engine *e, const char *path, float sample_proportion, uint32_t *out_n);
 
 /*
  * The solve step: replaces the body of vec_query (include/baseline.hpp:88-177).  queries: m x 104

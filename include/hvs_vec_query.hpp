@@ -51,9 +51,15 @@ inline void flatten(const std::vector<std::vector<float>> &rows, size_t width, s
 inline void vec_query(std::vector<std::vector<float>> &nodes, std::vector<std::vector<float>> &queries,
                       float sample_proportion, std::vector<std::vector<uint32_t>> &knn_results)
 {
-    std::vector<float> d, q;
-    hvs_shim::flatten(nodes, HVS_DATA_ROW, d);
+    // D goes to the device straight from the nested vectors (hvs_index_build_rows streams the N heap rows through
+    // pinned staging buffers); only the small query set is flattened here
+    std::vector<float> q;
     hvs_shim::flatten(queries, HVS_QUERY_ROW, q);
+    std::vector<const float *> rows(nodes.size());
+    for (size_t i = 0; i < nodes.size(); ++i) {
+        if (nodes[i].size() < HVS_DATA_ROW) { std::fprintf(stderr, "hvs vec_query: data row %zu has %zu floats, expected 102\n", i, nodes[i].size()); std::abort(); }
+        rows[i] = nodes[i].data();
+    }
     hvs_engine *e = nullptr;
     hvs_config cfg;
     std::memset(&cfg, 0, sizeof cfg);
@@ -62,7 +68,7 @@ inline void vec_query(std::vector<std::vector<float>> &nodes, std::vector<std::v
     cfg.mode = HVS_MODE_AUTO;
     if (const char *m = std::getenv("HVS_MODE")) cfg.mode = (uint32_t)std::atoi(m);
     if (hvs_create(&e, &cfg) != HVS_OK) hvs_shim::die(nullptr, "hvs_create");
-    if (hvs_index_build(e, d.data(), (uint32_t)nodes.size(), sample_proportion) != HVS_OK) hvs_shim::die(e, "hvs_index_build");
+    if (hvs_index_build_rows(e, rows.data(), (uint32_t)nodes.size(), sample_proportion) != HVS_OK) hvs_shim::die(e, "hvs_index_build_rows");
     const uint32_t m = (uint32_t)queries.size();
     std::vector<uint32_t> ids((size_t)m * HVS_K);
     if (hvs_solve(e, q.data(), m, ids.data()) != HVS_OK) hvs_shim::die(e, "hvs_solve");

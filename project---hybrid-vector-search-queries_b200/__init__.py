@@ -35,6 +35,7 @@ HVS_OK, HVS_ERR_INVALID, HVS_ERR_NO_DEVICE, HVS_ERR_CUDA, HVS_ERR_STATE, HVS_ERR
 # every symbol include/hvs.h declares (tests check the library exports exactly these)
 ABI_SYMBOLS = (
     "hvs_abi_version", "hvs_last_error", "hvs_create", "hvs_destroy", "hvs_index_build", "hvs_index_build_device",
+    "hvs_index_build_rows", "hvs_index_build_from_file",
     "hvs_solve", "hvs_solve_device", "hvs_solve_partial_device", "hvs_merge_partials_device", "hvs_rescore",
     "hvs_get_stats", "hvs_measure_ffma_peak", "hvs_plan_dryrun",
 )
@@ -95,6 +96,10 @@ def lib():
             f = getattr(L, name)
             f.restype = i32
             f.argtypes = [vp, vp, u32, f32]
+        L.hvs_index_build_rows.restype = i32
+        L.hvs_index_build_rows.argtypes = [vp, vp, u32, f32]
+        L.hvs_index_build_from_file.restype = i32
+        L.hvs_index_build_from_file.argtypes = [vp, C.c_char_p, f32, C.POINTER(u32)]
         for name in ("hvs_solve", "hvs_solve_device"):
             f = getattr(L, name)
             f.restype = i32
@@ -170,6 +175,12 @@ class Engine:
         else:
             a = _host_f32(nodes, DROW)
             self._ck(lib().hvs_index_build(self._h, a.ctypes.data, a.shape[0], sample_proportion))
+
+    def index_build_from_file(self, path: str, sample_proportion: float = 1.0) -> int:
+        """Index the D file directly (reference layout, README.md:32-44); returns the row count."""
+        n = C.c_uint32()
+        self._ck(lib().hvs_index_build_from_file(self._h, os.fsencode(path), sample_proportion, C.byref(n)))
+        return n.value
 
     # ---- solve step ----
     def solve(self, queries, out: np.ndarray | None = None) -> np.ndarray:

@@ -106,7 +106,7 @@ extern "C" void hvs_destroy(hvs_engine *e)
                       &e->d_qoff, &e->d_qlists, &e->d_cand, &e->d_cand_cnt, &e->d_scratch, &e->d_flags, &e->d_gthr, &e->d_pool, &e->d_gbest, &e->d_glock,
                       &e->d_work_counter, &e->d_rescore_ids, &e->d_rescore_out};
     for (DevBuf *b : bufs) b->release();
-    e->h_slices.release(); e->h_stage.release();
+    e->h_slices.release(); e->h_stage.release(); e->h_ingest[0].release(); e->h_ingest[1].release();
     for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : e->evg) if (ev) cudaEventDestroy(ev);
     for (auto &ev : e->ev_sync) if (ev) cudaEventDestroy(ev);
@@ -140,25 +140,6 @@ extern "C" int hvs_index_build_device(hvs_engine *e, const float *rows_dev, uint
     e->stats.n = e->index.n;
     e->stats.n_total = e->index.n_total;
     return HVS_OK;
-}
-
-extern "C" int hvs_index_build(hvs_engine *e, const float *rows_host, uint32_t n, float sample_proportion)
-{
-    if (!e) return HVS_ERR_INVALID;
-    e->err.clear();
-    if (!rows_host) EFAIL(HVS_ERR_INVALID, "hvs_index_build: rows is NULL");
-    if (n < HVS_K)
-        EFAIL(HVS_ERR_INVALID, "hvs_index_build: n < 100 (the reference's pad rule reads nodes[n-s], include/baseline.hpp:138-147)");
-    ECUDA(cudaSetDevice(e->device));
-    DevBuf rows;
-    size_t bytes = (size_t)n * DROW * 4;
-    if (rows.ensure(bytes) != cudaSuccess) { cudaGetLastError(); EFAIL(HVS_ERR_NOMEM, "hvs_index_build: device allocation for D failed"); }
-    cudaError_t c = cudaMemcpyAsync(rows.p, rows_host, bytes, cudaMemcpyHostToDevice, e->stream);
-    if (c == cudaSuccess) c = cudaStreamSynchronize(e->stream);
-    if (c != cudaSuccess) { rows.release(); e->err = std::string("hvs_index_build: H2D of D: ") + cudaGetErrorString(c); return HVS_ERR_CUDA; }
-    int rc = hvs_index_build_device(e, rows.as<float>(), n, sample_proportion);
-    rows.release();
-    return rc;
 }
 
 // ---- solve ----------------------------------------------------------------------------------

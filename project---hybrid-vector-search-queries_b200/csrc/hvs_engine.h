@@ -154,7 +154,7 @@ struct hvs_engine {
     // per-solve scratch (grow-only)
     hvs::DevBuf d_queries, d_out, d_slices, d_direct_q, d_items, d_item_q, d_tile_q, d_qoff, d_qlists;
     hvs::DevBuf d_cand, d_cand_cnt, d_scratch, d_flags, d_gthr, d_pool, d_gbest, d_glock, d_work_counter, d_rescore_ids, d_rescore_out;
-    hvs::HostPinned h_slices, h_stage;
+    hvs::HostPinned h_slices, h_stage, h_ingest[2];
     cudaEvent_t ev[12]{};
     cudaEvent_t evg[16]{};     // start/end of each group's tile launch
     hvs::Plan plan;

@@ -276,3 +276,35 @@ def test_cpp_driver_same_files_same_bytes(H, oracle, check, datagen, tmp_path):
         dist = np.fromfile(f, np.float32).reshape(m, 100)
     assert m == len(q)
     assert np.array_equal(dist.view(np.uint32), oracle.rescore(d, q, ids).view(np.uint32))
+
+
+def test_index_build_from_file_and_rows(H, oracle, check, datagen, tmp_path):
+    """The streaming ingest entry points must index exactly what hvs_index_build indexes:
+    from the D file (reference layout) and -- through the C++ driver test above -- from N row pointers."""
+    d = datagen.gen_data(70_000, 81, ncat=9)       # 28.6 MB: less than one 64 MB staging chunk ...
+    q = datagen.gen_queries(150, 82, ncat=9)
+    path = str(tmp_path / "d.bin")
+    datagen.write_bin(path, d)
+    with H.Engine(mode=H.MODE_AUTO) as e:
+        e.index_build(d)
+        want = e.solve(q)
+    with H.Engine(mode=H.MODE_AUTO) as e:
+        assert e.index_build_from_file(path) == len(d)
+        got = e.solve(q)
+        with pytest.raises(H.HvsError):
+            e.index_build_from_file(str(tmp_path / "missing.bin"))
+    assert np.array_equal(got, want)
+    big = datagen.gen_data(400_000, 83, ncat=9)    # ... and 163 MB: three chunks, rows straddle chunk borders
+    bpath = str(tmp_path / "big.bin")
+    datagen.write_bin(bpath, big)
+    with H.Engine(mode=H.MODE_EXACT) as e:
+        e.index_build_from_file(bpath)
+        got = e.solve(q)
+    ref = oracle.vec_query(big, q[:40], want_dist=False)
+    p = check.compare(big, q[:40], ref, got[:40], rtol=RTOL)
+    assert p.ok and p.dist_bit_identical_rows == 40, p.summary()
+    with open(bpath, "r+b") as f:                  # a file shorter than its header says is refused, not read past
+        f.truncate(4 + 102 * 4 * 1000)
+    with H.Engine() as e:
+        with pytest.raises(H.HvsError):
+            e.index_build_from_file(bpath)
