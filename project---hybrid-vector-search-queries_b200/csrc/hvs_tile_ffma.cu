@@ -186,26 +186,36 @@ k_tile_ffma(const float *__restrict__ queries, const QSlice *__restrict__ slices
         const bool interior = trow0 >= lo_max && trow0 + TR <= hi_min;
         uint64_t pend = 0;
         {
-            float thr[8];
+            float thr[8], xn[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) thr[j] = S.thr[wq * 32 + ly + 4 * j];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = wr * 64 + lx + 8 * i;
-                const float xn = S.xn[st][r];
-                const uint32_t row = trow0 + r;
+            for (int i = 0; i < 8; ++i) xn[i] = S.xn[st][wr * 64 + lx + 8 * i];
+            // scores first, branch-free; then ONE test per query (the minimum of its 8 rows in this thread): the
+            // element-wise look happens only where that minimum beats the threshold (rare after the warm-up)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float s = fmaf(-2.f, acc[i][j], xn);
+            for (int j = 0; j < 8; ++j) {
+                float m = __int_as_float(0x7f800000);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float s = fmaf(-2.f, acc[i][j], xn[i]);
                     acc[i][j] = s;
-                    bool ok = s < thr[j];
-                    if (!interior) ok = ok && row >= qlo[j] && row < qhi[j];
-                    if (ok) {
-                        const int qq = wq * 32 + ly + 4 * j;
-                        const uint32_t slot = atomicAdd(&S.bcnt[qq], 1u);
-                        if (slot < (uint32_t)CB) S.buf[qq][slot] = ((uint64_t)okey(s) << 32) | row;
-                        else pend |= 1ull << (i * 8 + j);
-                        if (slot >= (uint32_t)(CB / 2 - 1)) S.need[t % 3] = 1u;
+                    m = fminf(m, s);
+                }
+                if (m < thr[j]) {
+                    const int qq = wq * 32 + ly + 4 * j;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float s = acc[i][j];
+                        const uint32_t row = trow0 + wr * 64 + lx + 8 * i;
+                        bool ok = s < thr[j];
+                        if (!interior) ok = ok && row >= qlo[j] && row < qhi[j];
+                        if (ok) {
+                            const uint32_t slot = atomicAdd(&S.bcnt[qq], 1u);
+                            if (slot < (uint32_t)CB) S.buf[qq][slot] = ((uint64_t)okey(s) << 32) | row;
+                            else pend |= 1ull << (i * 8 + j);
+                            if (slot >= (uint32_t)(CB / 2 - 1)) S.need[t % 3] = 1u;
+                        }
                     }
                 }
             }
