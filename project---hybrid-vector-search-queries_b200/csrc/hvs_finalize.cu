@@ -15,7 +15,7 @@ namespace hvs {
 
 namespace {
 constexpr int FT = 128;        // threads
-constexpr int P1CAP = 2048;    // approximate-score selection buffer
+constexpr int P1CAP = 2048;    // approximate-score selection buffer (>= P1KEEP + 4 lists of KOUT)
 constexpr int P1KEEP = 512;    // most rows that may sit inside the margin before we give up
 struct FinSmem {
     TopBuf<P1CAP, true> p1;
@@ -47,20 +47,32 @@ k_finalize(const float *__restrict__ queries, const QSlice *__restrict__ slices,
                                          : margin_ffma(sl.qnorm, xnorm_max);
 
     // phase 1: the rows whose approximate score is within the margin of the global 100-th best
+    // Four lists per round, one warp each: the list lengths of a round are fetched together, so a query with
+    // 77 lists pays ~20 dependent round trips to L2 instead of 77.
     const uint32_t l0 = qoff[blockIdx.x], l1 = qoff[blockIdx.x + 1];
-    for (uint32_t li = l0; li < l1; ++li) {
-        const uint32_t list = qlists[li];
-        const uint32_t c = min(cand_cnt[list], (uint32_t)KOUT);
-        for (uint32_t e = tid; e < c; e += FT) {
-            const uint64_t k = cand[(size_t)list * KOUT + e];
-            const float s = okey_inv((uint32_t)(k >> 32));
-            if (s < S.p1.thr) {
-                const uint32_t slot = atomicAdd(&S.p1.cnt, 1u);
-                S.p1.cand[slot] = k;                         // cnt <= P1CAP - KOUT before every list
+    constexpr uint32_t LPR = FT / 32;
+    __shared__ uint32_t s_list[LPR], s_len[LPR];
+    const uint32_t warp = tid >> 5, lane = tid & 31;
+    for (uint32_t lb = l0; lb < l1; lb += LPR) {
+        if ((uint32_t)tid < LPR) {
+            uint32_t list = 0, c = 0;
+            if (lb + tid < l1) { list = qlists[lb + tid]; c = min(cand_cnt[list], (uint32_t)KOUT); }
+            s_list[tid] = list; s_len[tid] = c;
+        }
+        __syncthreads();
+        {
+            const uint32_t list = s_list[warp], c = s_len[warp];
+            for (uint32_t e = lane; e < c; e += 32) {
+                const uint64_t k = cand[(size_t)list * KOUT + e];
+                const float s = okey_inv((uint32_t)(k >> 32));
+                if (s < S.p1.thr) {
+                    const uint32_t slot = atomicAdd(&S.p1.cnt, 1u);
+                    S.p1.cand[slot] = k;                     // cnt <= P1CAP - LPR * KOUT before every round
+                }
             }
         }
         __syncthreads();
-        if (S.p1.cnt > (uint32_t)(P1CAP - KOUT)) S.p1.compact(tid, FT, margin, P1KEEP);
+        if (S.p1.cnt > (uint32_t)(P1CAP - LPR * KOUT)) S.p1.compact(tid, FT, margin, P1KEEP);
     }
     S.p1.compact(tid, FT, margin, P1KEEP);
     if (S.p1.overflow && tid == 0) flags[q] = 1u;            // K4 re-solves this query
