@@ -69,6 +69,7 @@ struct TensorSmem {
     alignas(8) uint64_t full[NST], empty[NST];
     alignas(8) uint64_t tfull[2][2], tempty[2][2];
     uint32_t tmem_base;
+    uint32_t cepoch[2];     // per query half: bumped by an epilogue warp that starts a compaction (the others join it)
 };
 
 // ---- tcgen05 wrappers ---------------------------------------------------------------------------
@@ -432,6 +433,7 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
         for (int s = 0; s < NST; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 2); }   // both MMA issuers release a stage
         for (int h = 0; h < 2; ++h)
             for (int b = 0; b < 2; ++b) { mbar_init(&S.tfull[h][b], 1); mbar_init(&S.tempty[h][b], 4); }
+        S.cepoch[0] = 0; S.cepoch[1] = 0;
         mbar_fence_init();
     }
     if (warp == 1) {                                                  // TMEM: all 512 columns, this warp owns them
@@ -445,7 +447,7 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
 
     long long c_mergeonly = 0, c_abuild = 0;
     long long c_wait = 0, c_scan = 0, c_compact = 0, c_merge = 0, c_mma_full = 0, c_mma_tempty = 0, c_items = 0;
-    unsigned n_compact = 0, n_surv = 0;
+    unsigned n_compact = 0, n_surv = 0, n_lhit = 0, n_whit = 0, n_infhit = 0, n_chunks = 0;
     const long long c_start = clock64();
     // running counters: the mbarrier phases continue across items
     uint32_t gt = 0;           // stages issued / consumed so far (producer, MMA)
@@ -555,8 +557,12 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
                 if (dbg == 4 && qslot < it.nq) st.thr = 0.f;        // measurement only: (almost) nothing survives
                 if (dbg == 5 && qslot < it.nq) st.thr = 3550.f;     // measurement only: steady-state-like survival rate ~1e-4
                 const uint32_t tlane = tmem + ((uint32_t)(quad * 32) << 16);
-                // 32 columns (data rows) at a time: four 8-wide minima, one compare; only a group whose minimum
-                // beats the threshold is looked at element by element
+                // 32 columns (data rows) at a time: four 8-wide minima, one compare and one warp vote; only when some
+                // lane of the warp has a group whose minimum beats its threshold is that group looked at element by
+                // element -- under warp-uniform branches, so lanes with hits in different groups do not serialise.
+                // thr_s = the lane's threshold for THIS stage: -inf while the stage lies outside the query's rows
+                // (a query whose slice starts later in the chunk must not send the warp down the slow path).
+                float thr_s = st.thr;
                 auto scan = [&](const uint32_t (&r)[32], uint32_t rbase) {
                     float g[4];
 #pragma unroll
@@ -567,15 +573,23 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
                         const float a3 = fminf(__uint_as_float(r[8 * q4 + 6]), __uint_as_float(r[8 * q4 + 7]));
                         g[q4] = fminf(fminf(a0, a1), fminf(a2, a3));
                     }
-                    if (fminf(fminf(g[0], g[1]), fminf(g[2], g[3])) < st.thr) {
+                    const bool hit = fminf(fminf(g[0], g[1]), fminf(g[2], g[3])) < thr_s;
+                    const bool whit = __any_sync(FULL, hit);
+                    if (kstat) {                                      // HVS_K3_STATS: how often the element-wise path runs
+                        ++n_chunks;
+                        n_lhit += hit ? 1u : 0u;
+                        n_infhit += (hit && st.thr == __int_as_float(0x7f800000)) ? 1u : 0u;
+                        n_whit += whit ? 1u : 0u;
+                    }
+                    if (whit) {
 #pragma unroll
                         for (int q4 = 0; q4 < 4; ++q4)
-                            if (g[q4] < st.thr) {
+                            if (__any_sync(FULL, g[q4] < thr_s)) {
 #pragma unroll
                                 for (int c = 8 * q4; c < 8 * q4 + 8; ++c) {
                                     const float s = __uint_as_float(r[c]);
                                     const uint32_t row = rbase + c;
-                                    if (s < st.thr && row >= st.qlo && row < st.qhi)
+                                    if (s < thr_s && row >= st.qlo && row < st.qhi)
                                         mypool[(size_t)32 * st.cnt++] = ((uint64_t)okey(s) << 32) | row;
                                 }
                             }
@@ -583,10 +597,20 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
                 };
                 // room for 32 more survivors in every pool of this warp; when one pool is nearly full (or a query has
                 // no threshold yet) all 32 queries of the warp are compacted together
-                auto make_room = [&]() {
-                    if (dbg >= 3) { if (st.cnt > (uint32_t)(POOL - 32)) st.cnt = 0; return; }   // measurement only
-                    if (__any_sync(FULL, st.cnt > (uint32_t)(POOL - 32) ||
-                                             (st.cnt >= 192u && st.thr == __int_as_float(0x7f800000)))) {
+                // The four warps of a half hand accumulators back together, so a warp that stops to compact stalls the
+                // other three.  They therefore compact TOGETHER: the warp that has to (a pool nearly full, or a query
+                // without a threshold yet) bumps the half's epoch, and the others join as soon as they see it if they
+                // hold enough survivors for it to be worthwhile -- the stalls overlap instead of adding up.
+                uint32_t my_ep = *reinterpret_cast<volatile uint32_t *>(&S.cepoch[h]);
+                auto make_room = [&](uint32_t slack) {
+                    if (dbg >= 3) { if (st.cnt > (uint32_t)POOL - slack) st.cnt = 0; return; }   // measurement only
+                    const uint32_t ep = *reinterpret_cast<volatile uint32_t *>(&S.cepoch[h]);
+                    const bool own = __any_sync(FULL, st.cnt > (uint32_t)POOL - slack ||
+                                                          (st.cnt >= 192u && st.thr == __int_as_float(0x7f800000)));
+                    const bool join = ep != my_ep && __any_sync(FULL, st.cnt >= 160u);
+                    if (own && ep == my_ep) { if (lane == 0) atomicAdd(&S.cepoch[h], 1u); my_ep = ep + 1; }
+                    else my_ep = ep;
+                    if (own || join) {
                         const long long t0 = clock64();
                         n_surv += st.cnt;
                         const uint2 o = compact_warp(st.cnt, st.thr, st.margin, st.qid, qslot < it.nq, pool_warp, gthr, flags, KOUT, lane);
@@ -595,10 +619,12 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
                         c_compact += clock64() - t0; ++n_compact;
                     }
                 };
+                uint32_t gpre = 0xff800000u;                             // okey(+inf)
                 for (uint32_t t = 0; t < ntiles; ++t) {
                     const uint32_t u = ga[h] + t;
-                    // a look at what other CTAs found out about this query
-                    if ((t & 7) == 7 && qslot < it.nq && dbg < 3) st.thr = fminf(st.thr, okey_inv(ld_relaxed_u32(&gthr[st.qid])));
+                    // a look at what other CTAs found out about this query: the load is issued one stage before its use
+                    if ((t & 7) == 7) st.thr = fminf(st.thr, okey_inv(gpre));
+                    if ((t & 7) == 6 && qslot < it.nq && dbg < 3) gpre = ld_relaxed_u32(&gthr[st.qid]);
                     const int b = u & 1;
                     { const long long t0 = clock64(); mbar_wait(&S.tfull[h][b], (u >> 1) & 1); c_wait += clock64() - t0; }
                     const long long ts0 = clock64();
@@ -606,26 +632,30 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
                     const uint32_t tcol = tlane + (uint32_t)(h * 2 + b) * TN;
                     const uint32_t trow0 = row0 + t * TN;
                     if (PIPE) {
-                        // two register sets: the TMEM load of the next 32 columns is in flight while these are scanned
+                        // whole stage unrolled: column offsets are immediates, one room check per stage (128 slots),
+                        // the TMEM load of the next 32 columns is in flight while these are scanned
+                        make_room(128u);
+                        thr_s = (trow0 < st.qhi && trow0 + TN > st.qlo) ? st.thr : __int_as_float(0xff800000);
                         uint32_t ra[32], rb[32];
                         tmem_ld32(tcol, ra);
-#pragma unroll 1
-                        for (int c4 = 0; c4 < TN / 32; c4 += 2) {
-                            make_room();
-                            tmem_wait_ld();
-                            tmem_ld32(tcol + (c4 + 1) * 32, rb);
-                            scan(ra, trow0 + c4 * 32);
-                            make_room();
-                            tmem_wait_ld();
-                            if (c4 + 2 < TN / 32) tmem_ld32(tcol + (c4 + 2) * 32, ra);
-                            scan(rb, trow0 + (c4 + 1) * 32);
-                        }
+                        tmem_wait_ld();
+                        tmem_ld32(tcol + 32, rb);
+                        scan(ra, trow0);
+                        tmem_wait_ld();
+                        tmem_ld32(tcol + 64, ra);
+                        scan(rb, trow0 + 32);
+                        tmem_wait_ld();
+                        tmem_ld32(tcol + 96, rb);
+                        scan(ra, trow0 + 64);
+                        tmem_wait_ld();
+                        scan(rb, trow0 + 96);
                     } else if (dbg == 0) {
 #pragma unroll 1
                         for (int c4 = 0; c4 < TN / 32; ++c4) {
                             uint32_t r[32];
                             tmem_ld32(tcol + c4 * 32, r);
-                            make_room();
+                            make_room(32u);
+                            thr_s = (trow0 < st.qhi && trow0 + TN > st.qlo) ? st.thr : __int_as_float(0xff800000);
                             tmem_wait_ld();
                             scan(r, trow0 + c4 * 32);
                         }
@@ -686,7 +716,11 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
         const long long c_total = clock64() - c_start;
         if (warp >= 2 && warp < 10) {
             n_surv = __reduce_add_sync(FULL, n_surv);
+            n_lhit = __reduce_add_sync(FULL, n_lhit);
+            n_infhit = __reduce_add_sync(FULL, n_infhit);
             if (lane == 0) {
+                atomicAdd(&kstat[16], (unsigned long long)n_chunks); atomicAdd(&kstat[17], (unsigned long long)n_whit);
+                atomicAdd(&kstat[18], (unsigned long long)n_lhit); atomicAdd(&kstat[19], (unsigned long long)n_infhit);
                 atomicAdd(&kstat[0], (unsigned long long)c_total); atomicAdd(&kstat[1], (unsigned long long)c_wait);
                 atomicAdd(&kstat[2], (unsigned long long)c_scan); atomicAdd(&kstat[3], (unsigned long long)c_compact);
                 atomicAdd(&kstat[4], (unsigned long long)c_merge); atomicAdd(&kstat[5], (unsigned long long)c_items);
@@ -743,7 +777,7 @@ cudaError_t launch_tile_tensor(hvs_engine *e, const float *queries_dev, const QS
         cudaMemsetAsync(e->d_scratch.p, 0, 256, e->stream);
         kstat = e->d_scratch.as<unsigned long long>();
     }
-    static const bool pipe = [] { const char *v = getenv("HVS_K3_PIPE"); return v && v[0] == '1'; }();
+    static const bool pipe = [] { const char *v = getenv("HVS_K3_PIPE"); return !(v && v[0] == '0'); }();   // default: pipelined, unrolled stage scan
     static const int dbg = [] { const char *v = getenv("HVS_K3_DBG"); return v ? atoi(v) : 0; }();
     auto kern = pipe ? k_tile_tensor<true> : k_tile_tensor<false>;
     kern<<<grid, NTHR, smem, e->stream>>>(queries_dev, slices_dev, items_dev + item_begin, n_items, item_q_dev,
@@ -752,10 +786,12 @@ cudaError_t launch_tile_tensor(hvs_engine *e, const float *queries_dev, const QS
                                           e->d_glock.as<uint32_t>() + e->stats.m, e->d_glock.as<uint32_t>() + 2 * (size_t)e->stats.m,
                                           e->d_glock.as<uint32_t>(), flags_dev, dbg, kstat);
     if (kstat) {
-        unsigned long long h[16];
+        unsigned long long h[20];
         cudaStreamSynchronize(e->stream);
         cudaMemcpy(h, kstat, sizeof h, cudaMemcpyDeviceToHost);
         const double ew = (double)h[8], mw = (double)h[12];
+        fprintf(stderr, "K3 hits: 32-column scans/warp %.0f, with a hit in the warp %.1f %%, lane hits per scan %.3f (with no threshold yet %.3f)\n",
+                h[16] / ew, 100.0 * h[17] / (double)(h[16] ? h[16] : 1), h[18] / (double)(h[16] ? h[16] : 1), h[19] / (double)(h[16] ? h[16] : 1));
         fprintf(stderr, "K3 stats per epilogue warp (Mcycles): total %.2f  wait_tfull %.2f  scan %.2f  (of which compact %.2f, n=%.1f)  item_end %.2f (merge_global %.2f)  A-build %.2f  barrier %.2f | survivors/warp %.0f | MMA warp: total %.2f wait_full %.2f wait_tempty %.2f\n",
                 h[0] / ew / 1e6, h[1] / ew / 1e6, h[2] / ew / 1e6, h[3] / ew / 1e6, h[6] / ew, h[4] / ew / 1e6, h[13] / ew / 1e6, h[14] / ew / 1e6, h[5] / ew / 1e6, h[7] / ew,
                 h[9] / mw / 1e6, h[10] / mw / 1e6, h[11] / mw / 1e6);
