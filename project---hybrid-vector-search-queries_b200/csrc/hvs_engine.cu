@@ -7,6 +7,8 @@
 // library; the host only plans.
 #include <algorithm>
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -89,6 +91,8 @@ extern "C" int hvs_create(hvs_engine **out, const hvs_config *cfg)
     for (auto &ev : e->evg) cudaEventCreate(&ev);
     for (auto &ev : e->ev_sync) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&e->stream_up, cudaStreamNonBlocking);
+    for (auto &ev : e->ev_up) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     e->stats.struct_size = sizeof(hvs_stats);
     *out = e;
     return HVS_OK;
@@ -111,6 +115,8 @@ extern "C" void hvs_destroy(hvs_engine *e)
     for (auto &ev : e->evg) if (ev) cudaEventDestroy(ev);
     for (auto &ev : e->ev_sync) if (ev) cudaEventDestroy(ev);
     if (e->stream2) cudaStreamDestroy(e->stream2);
+    if (e->stream_up) cudaStreamDestroy(e->stream_up);
+    for (auto &ev : e->ev_up) if (ev) cudaEventDestroy(ev);
     if (e->own_stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -180,13 +186,14 @@ static int solve_impl(hvs_engine *e, const float *q_dev, uint32_t m, bool partia
     ECUDA(e->h_stage.ensure(P.direct_q.size() * 4 + max_items * sizeof(TileItem) + (size_t)P.incid * 8 + (size_t)m * 12 + 1024));
     unsigned char *hs = e->h_stage.as<unsigned char>();
     size_t o = 0;
-    auto up_at = [&](void *dst, const void *src, size_t bytes) -> cudaError_t {
+    auto up_on = [&](cudaStream_t st_, void *dst, const void *src, size_t bytes) -> cudaError_t {
         if (!bytes) return cudaSuccess;
         std::memcpy(hs + o, src, bytes);
-        cudaError_t c = cudaMemcpyAsync(dst, hs + o, bytes, cudaMemcpyHostToDevice, s);
+        cudaError_t c = cudaMemcpyAsync(dst, hs + o, bytes, cudaMemcpyHostToDevice, st_);
         o += (bytes + 15) & ~(size_t)15;
         return c;
     };
+    auto up_at = [&](void *dst, const void *src, size_t bytes) -> cudaError_t { return up_on(s, dst, src, bytes); };
     ECUDA(e->d_direct_q.ensure(P.direct_q.size() * 4 + 16));
     ECUDA(up_at(e->d_direct_q.p, P.direct_q.data(), P.direct_q.size() * 4));
     cudaEventRecord(e->ev[3], s);
@@ -214,21 +221,26 @@ static int solve_impl(hvs_engine *e, const float *q_dev, uint32_t m, bool partia
         st.launches++;
         if (P.tensor) ECUDA(tile_tensor_begin(e));
         TileItem *d_items = e->d_items.as<TileItem>();
+        cudaEventRecord(e->ev_sync[0], s);                         // setup of this solve is enqueued up to here
         for (size_t g = 0; g < n_groups; ++g) {
             uint32_t ib = 0, ie = 0;
             const size_t iq0 = P.item_q.size();
             plan_group(h_sl, P, g, ib, ie);
             if (ie == ib) continue;
             if (ie > max_items) EFAIL(HVS_ERR_STATE, "planner produced more items than it announced");
-            ECUDA(up_at(d_items + ib, P.items.data() + ib, (size_t)(ie - ib) * sizeof(TileItem)));
-            ECUDA(up_at(e->d_item_q.as<uint32_t>() + iq0, P.item_q.data() + iq0, (P.item_q.size() - iq0) * 4));
+            // The work lists go up on their own stream: queued on a launch lane they would wait for the sweep
+            // running there, and the next group could not start before the previous one had drained.
+            cudaStream_t su = e->stream_up && g < 8 ? e->stream_up : s;
+            ECUDA(up_on(su, d_items + ib, P.items.data() + ib, (size_t)(ie - ib) * sizeof(TileItem)));
+            ECUDA(up_on(su, e->d_item_q.as<uint32_t>() + iq0, P.item_q.data() + iq0, (P.item_q.size() - iq0) * 4));
             // odd groups run on a second stream with their own survivor pools, so that the tail of one launch
             // (CTAs running out of items) overlaps the head of the next
             cudaStream_t sg = (g & 1) && e->stream2 ? e->stream2 : s;
-            if (sg != s) {
-                cudaEventRecord(e->ev_sync[0], s);                 // everything enqueued so far: setup + this group's uploads
-                ECUDA(cudaStreamWaitEvent(sg, e->ev_sync[0], 0));
+            if (su != s) {
+                cudaEventRecord(e->ev_up[g], su);
+                ECUDA(cudaStreamWaitEvent(sg, e->ev_up[g], 0));
             }
+            if (sg != s) ECUDA(cudaStreamWaitEvent(sg, e->ev_sync[0], 0));   // the solve's setup (memsets, fills) on the main lane
             e->pool_slot = (uint32_t)(g & 1);
             cudaStream_t saved = e->stream;
             e->stream = sg;
@@ -298,6 +310,14 @@ static int solve_impl(hvs_engine *e, const float *q_dev, uint32_t m, bool partia
         st.ms_finalize = ev_ms(e->ev[7], e->ev[8]);
     }
     st.ms_solve_device = ev_ms(e->ev[2], e->ev[9]);
+    static const bool timeline = getenv("HVS_TIMELINE") != nullptr;
+    if (timeline) {                                  // developer aid: when each phase ran, ms since the start of the solve
+        fprintf(stderr, "timeline: plan end %.2f  direct end %.2f ", ev_ms(e->ev[2], e->ev[3]), ev_ms(e->ev[2], e->ev[4]));
+        for (size_t g = 0; g < n_groups && g < 8; ++g)
+            if (ran[g]) fprintf(stderr, " group %zu [%.2f, %.2f]", g, ev_ms(e->ev[2], e->evg[2 * g]), ev_ms(e->ev[2], e->evg[2 * g + 1]));
+        if (any_items) fprintf(stderr, "  finalize [%.2f, %.2f]", ev_ms(e->ev[2], e->ev[7]), ev_ms(e->ev[2], e->ev[8]));
+        fprintf(stderr, "  end %.2f\n", st.ms_solve_device);
+    }
     return HVS_OK;
 }
 

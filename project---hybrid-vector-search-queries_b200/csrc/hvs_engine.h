@@ -145,7 +145,10 @@ struct hvs_engine {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaStream_t stream2 = nullptr;   // second lane for tile launches: the tail of group g overlaps the head of group g + 1
+    cudaStream_t stream_up = nullptr; // work-list uploads of the groups: never queued behind a running sweep
     cudaEvent_t ev_sync[4]{};
+    cudaEvent_t ev_up[8]{};           // upload of group g done
+    uint32_t work_slot = 0;           // which item counter (d_work_counter) the next K3 launch draws from
     uint32_t pool_slot = 0;           // which half of the survivor pools the next K3 launch uses
     int sm_count = 148;
     std::string err;

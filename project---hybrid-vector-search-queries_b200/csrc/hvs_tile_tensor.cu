@@ -34,6 +34,7 @@
 // the epilogue must read the 128 KB of fp32 accumulators of a stage out of TMEM (the measured limit
 // of this design: ~1000 cycles per stage per SM sub-partition pair); the B stream is 28,672 B per
 // stage per SM.  HVS_K3_STATS=1 prints the cycle budget per warp role.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 
@@ -69,6 +70,7 @@ struct TensorSmem {
     alignas(8) uint64_t full[NST], empty[NST];
     alignas(8) uint64_t tfull[2][2], tempty[2][2];
     uint32_t tmem_base;
+    uint32_t next_item;     // dynamic work distribution: the item this CTA sweeps next
     uint32_t cepoch[2];     // per query half: bumped by an epilogue warp that starts a compaction (the others join it)
 };
 
@@ -127,12 +129,31 @@ struct QState {
     uint32_t cnt, qlo, qhi, qid;
 };
 
+// Next probe of the rank search shared by compact_warp and merge_global: a score v between the bracket ends
+// (#{<= klo} = clo < K <= chi = #{<= khi}).  The survivors sit in the lower tail of the score distribution, where the
+// count grows roughly exponentially with the score, so the probe interpolates log(count) linearly -- in the FLOAT
+// domain (order-preserving keys are very non-linear around zero) -- and every third step bisects the key interval,
+// which bounds the worst case.  Measured on pools of 192..480 tail scores: ~3 probes instead of 9-18 with linear
+// interpolation on the keys.
+__device__ __forceinline__ uint32_t select_probe(uint32_t klo, uint32_t khi, uint32_t clo, uint32_t chi, int it)
+{
+    uint32_t mid;
+    if (it % 3 == 2) mid = klo + ((khi - klo) >> 1);
+    else {
+        const float flo = okey_inv(klo), fhi = okey_inv(khi);
+        const float a = __logf(fmaxf((float)clo, 0.5f)), b = __logf((float)chi);
+        const float t = (__logf((float)(K + 4)) - a) / fmaxf(b - a, 1e-6f);
+        mid = okey(flo + (fhi - flo) * fminf(fmaxf(t, 0.f), 1.f));
+    }
+    return min(max(mid, klo + 1u), khi - 1u);
+}
+
 // Pools are transposed: entry i of the query owned by lane l lives at pool_warp[i * 32 + l], so that the
 // 32 lanes of a warp walk their 32 pools in lock step with fully coalesced loads.
 //
 // Lane-parallel compaction: every lane that holds at least K survivors searches, privately, for a score v
 // with  K <= #{entries <= v} <= K + 8  (any v with at least K entries at or below it bounds the final K-th
-// best; the search is regula falsi on the counting function with a bisection step every third pass), then
+// best; the search brackets the rank with select_probe, a bisection step every third pass), then
 // rewrites its pool keeping only the entries within `margin` of v and tightens its threshold.
 // One call serves up to 32 queries; no sorting, no shuffles, a handful of coalesced passes over the pools.
 __device__ __noinline__ uint2 compact_warp(uint32_t cnt, float thr, float margin, uint32_t qid, bool valid,
@@ -143,34 +164,37 @@ __device__ __noinline__ uint2 compact_warp(uint32_t cnt, float thr, float margin
     const uint32_t maxc = __reduce_max_sync(FULL, part ? cnt : 0u);
     if (maxc == 0) return make_uint2(cnt, __float_as_uint(thr));
     const uint32_t *sc = reinterpret_cast<const uint32_t *>(pool_warp) + 2 * lane + 1;   // score word of entry i: sc[64 i]
-    uint32_t klo = 0xffffffffu, khi = 0u;                             // range of the scores
+    // First pass: range of the scores, and the count at a first probe -- the bound the previous compaction left
+    // (thr - margin still has at least K entries at or below it; with no threshold yet the probe counts nothing).
+    const uint32_t g0 = thr < __int_as_float(0x7f800000) ? okey(thr - margin) : 0u;
+    uint32_t klo = 0xffffffffu, khi = 0u, cg = 0u;
     for (uint32_t i0 = 0; i0 < maxc; i0 += 32) {                      // 32 independent loads in flight per lane
         uint32_t k[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) k[j] = __ldcg(sc + (size_t)64 * (i0 + j));
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-            if (part && i0 + j < cnt) { klo = min(klo, k[j]); khi = max(khi, k[j]); }
+            if (part && i0 + j < cnt) { klo = min(klo, k[j]); khi = max(khi, k[j]); cg += k[j] <= g0 ? 1u : 0u; }
     }
     // invariant: #{<= klo} = clo < K <= chi = #{<= khi}
     bool done = !part || klo == khi;
     uint32_t clo = 0, chi = cnt;
-    if (!done) klo -= 1;
-    for (int it = 0; it < 40 && !__all_sync(FULL, done); ++it) {
-        uint32_t mid;
-        if (it % 3 == 2) mid = klo + ((khi - klo) >> 1);
-        else {
-            const unsigned long long num = (unsigned long long)(khi - klo) * (uint32_t)(K + 4 - clo);
-            mid = klo + (uint32_t)(num / max(chi - clo, 1u));
+    if (!done) {
+        klo -= 1;
+        if (g0 > klo && g0 < khi) {
+            if (cg >= (uint32_t)K) { khi = g0; chi = cg; done = cg <= (uint32_t)K + 8u; }
+            else { klo = g0; clo = cg; }
         }
-        mid = min(max(mid, klo + 1u), khi - 1u);
+    }
+    for (int it = 0; it < 40 && !__all_sync(FULL, done); ++it) {
+        const uint32_t mid = select_probe(klo, khi, clo, chi, it);
         uint32_t c = 0;
-        for (uint32_t i0 = 0; i0 < maxc; i0 += 32) {
-            uint32_t k[32];
+        for (uint32_t i0 = 0; i0 < maxc; i0 += 64) {                  // 64 independent loads in flight per lane
+            uint32_t k[64];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) k[j] = __ldcg(sc + (size_t)64 * (i0 + j));
+            for (int j = 0; j < 64; ++j) k[j] = __ldcg(sc + (size_t)64 * (i0 + j));
 #pragma unroll
-            for (int j = 0; j < 32; ++j) c += (i0 + j < cnt && k[j] <= mid) ? 1u : 0u;
+            for (int j = 0; j < 64; ++j) c += (i0 + j < cnt && k[j] <= mid) ? 1u : 0u;
         }
         if (!done) {
             if (c >= (uint32_t)K) { khi = mid; chi = c; done = c <= (uint32_t)K + 8u; }
@@ -183,13 +207,15 @@ __device__ __noinline__ uint2 compact_warp(uint32_t cnt, float thr, float margin
     uint32_t limk = 0xffffffffu;
     if (part) { lim = okey_inv(khi) + margin; limk = okey(lim); }
     uint32_t w = 0;
-    for (uint32_t i0 = 0; i0 < maxc; i0 += 16) {
-        uint64_t e[16];
+    for (uint32_t i0 = 0; i0 < maxc; i0 += 32) {
+        uint64_t e[32];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) e[j] = __ldcg(pool_warp + (size_t)32 * (i0 + j) + lane);
+        for (int j = 0; j < 32; ++j) e[j] = __ldcg(pool_warp + (size_t)32 * (i0 + j) + lane);
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-            if (part && i0 + j < cnt && (uint32_t)(e[j] >> 32) <= limk) { pool_warp[(size_t)32 * w + lane] = e[j]; ++w; }
+        for (int j = 0; j < 32; ++j) {
+            const uint32_t kj = (uint32_t)(e[j] >> 32);
+            if (part && i0 + j < cnt && kj <= limk) { pool_warp[(size_t)32 * w + lane] = e[j]; ++w; }
+        }
     }
     if (part) {
         if (w > keep_cap) {                                           // more rows inside the margin than a list may hold:
@@ -303,13 +329,7 @@ __device__ __noinline__ float merge_global(uint32_t cnt, float thr, float margin
     uint32_t clo = 0, chi = gn + cnt;
     if (!done) klo -= 1;
     for (int it = 0; it < 40 && !__all_sync(FULL, done); ++it) {
-        uint32_t mid;
-        if (it % 3 == 2) mid = klo + ((khi - klo) >> 1);
-        else {
-            const unsigned long long num = (unsigned long long)(khi - klo) * (uint32_t)(K + 4 - clo);
-            mid = klo + (uint32_t)(num / max(chi - clo, 1u));
-        }
-        mid = min(max(mid, klo + 1u), khi - 1u);
+        const uint32_t mid = select_probe(klo, khi, clo, chi, it);
         uint32_t c = 0;
         for (uint32_t i0 = 0; i0 < maxg; i0 += 16) {
             uint32_t k[16];
@@ -423,7 +443,8 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
               const unsigned char *__restrict__ img1, float xnorm_max, float sx, uint64_t *__restrict__ pool,
               uint64_t *__restrict__ cand, uint32_t *__restrict__ cand_cnt, uint32_t *__restrict__ gthr,
               uint32_t *__restrict__ gbest, uint32_t *__restrict__ gcnt, uint32_t *__restrict__ gcut,
-              uint32_t *__restrict__ glock, uint32_t *__restrict__ flags, int dbg, unsigned long long *__restrict__ kstat)
+              uint32_t *__restrict__ glock, uint32_t *__restrict__ flags, uint32_t *__restrict__ work_counter, int dbg,
+              unsigned long long *__restrict__ kstat)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TensorSmem &S = *reinterpret_cast<TensorSmem *>(smem_raw);
@@ -434,6 +455,7 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
         for (int h = 0; h < 2; ++h)
             for (int b = 0; b < 2; ++b) { mbar_init(&S.tfull[h][b], 1); mbar_init(&S.tempty[h][b], 4); }
         S.cepoch[0] = 0; S.cepoch[1] = 0;
+        S.next_item = atomicAdd(work_counter, 1u);
         mbar_fence_init();
     }
     if (warp == 1) {                                                  // TMEM: all 512 columns, this warp owns them
@@ -447,13 +469,17 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
 
     long long c_mergeonly = 0, c_abuild = 0;
     long long c_wait = 0, c_scan = 0, c_compact = 0, c_merge = 0, c_mma_full = 0, c_mma_tempty = 0, c_items = 0;
-    unsigned n_compact = 0, n_surv = 0, n_lhit = 0, n_whit = 0, n_infhit = 0, n_chunks = 0;
+    unsigned n_items_done = 0, n_compact = 0, n_surv = 0, n_lhit = 0, n_whit = 0, n_infhit = 0, n_chunks = 0;
     const long long c_start = clock64();
     // running counters: the mbarrier phases continue across items
     uint32_t gt = 0;           // stages issued / consumed so far (producer, MMA)
     uint32_t ga[2] = {0, 0};   // accumulator uses so far, per half (MMA, epilogue)
 
-    for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+    // Items are handed out dynamically, longest first (the planner sorts them): a CTA that draws expensive items
+    // (queries still warming up their thresholds) simply takes fewer of them.
+    for (;;) {
+        const uint32_t item = S.next_item;
+        if (item >= n_items) break;
         const TileItem it = items[item];
         const unsigned char *img = it.arena == ARENA_T ? img0 : img1;
         const int nhalf = it.nq > 128u ? 2 : 1;
@@ -489,6 +515,8 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
         fence_proxy_async();                                          // generic-proxy writes -> visible to the tensor core
         __syncthreads();
         c_abuild += clock64() - ta0;
+        uint32_t item_next = 0;
+        if (tid == 0) item_next = atomicAdd(work_counter, 1u);        // everybody has read next_item; the answer is awaited at the end of the item
 
         if (warp == 0) {
             // ===== TMA producer (whole warp runs the loop, one elected lane talks to the TMA engine) =====
@@ -503,6 +531,7 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
                 }
                 __syncwarp();
             }
+            if (tid == 0) S.next_item = item_next;
         } else if (warp == 1 || warp == 10) {
             // ===== MMA issuers: one warp per query half, warp-uniform control flow, one elected lane issues =====
             // Accumulator (half h, buffer b) = TMEM columns [128 (2h+b), +128): the epilogue drains buffer b of a
@@ -711,6 +740,7 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
         __syncthreads();                                              // item boundary: A may be rebuilt
         tc_fence_after();
         c_items += clock64() - t0; }
+        ++n_items_done;
     }
     if (kstat) {
         const long long c_total = clock64() - c_start;
@@ -719,6 +749,12 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
             n_lhit = __reduce_add_sync(FULL, n_lhit);
             n_infhit = __reduce_add_sync(FULL, n_infhit);
             if (lane == 0) {
+                atomicMax(&kstat[20], (unsigned long long)c_total);
+                if (warp == 2) {                                  // per-CTA record (first epilogue warp): who is slow, and why
+                    unsigned long long *r = kstat + 32 + 8 * blockIdx.x;
+                    r[0] = (unsigned long long)c_total; r[1] = n_items_done; r[2] = (unsigned long long)c_scan; r[3] = (unsigned long long)c_compact;
+                    r[4] = n_compact; r[5] = (unsigned long long)c_wait; r[6] = (unsigned long long)c_merge; r[7] = (unsigned long long)c_items;
+                }
                 atomicAdd(&kstat[16], (unsigned long long)n_chunks); atomicAdd(&kstat[17], (unsigned long long)n_whit);
                 atomicAdd(&kstat[18], (unsigned long long)n_lhit); atomicAdd(&kstat[19], (unsigned long long)n_infhit);
                 atomicAdd(&kstat[0], (unsigned long long)c_total); atomicAdd(&kstat[1], (unsigned long long)c_wait);
@@ -742,6 +778,11 @@ cudaError_t tile_tensor_begin(hvs_engine *e)
 {
     cudaError_t c = e->d_pool.ensure((size_t)2 * e->sm_count * QT_TENSOR * POOL * 8);   // two pool sets: launches on the two lanes overlap
     if (c != cudaSuccess) return c;
+    c = e->d_work_counter.ensure(64 * 4);                                                            // one item counter per launch of this solve
+    if (c != cudaSuccess) return c;
+    c = cudaMemsetAsync(e->d_work_counter.p, 0, 64 * 4, e->stream);
+    if (c != cudaSuccess) return c;
+    e->work_slot = 0;
     c = e->d_gbest.ensure((size_t)e->stats.m * GB * 4);
     if (c != cudaSuccess) return c;
     c = e->d_glock.ensure((size_t)e->stats.m * 12);                                                  // [m] locks, [m] counts, [m] K-th keys
@@ -769,12 +810,13 @@ cudaError_t launch_tile_tensor(hvs_engine *e, const float *queries_dev, const QS
     const Index &ix = e->index;
     const uint32_t grid = n_items < (uint32_t)e->sm_count ? n_items : (uint32_t)e->sm_count;
     cudaError_t c = cudaSuccess;
+    if (e->work_slot >= 63) return cudaErrorInvalidValue;
     static const bool want_stats = getenv("HVS_K3_STATS") != nullptr;
     unsigned long long *kstat = nullptr;
     if (want_stats) {
-        c = e->d_scratch.ensure(256);
+        c = e->d_scratch.ensure(256 + 64 * 256);
         if (c != cudaSuccess) return c;
-        cudaMemsetAsync(e->d_scratch.p, 0, 256, e->stream);
+        cudaMemsetAsync(e->d_scratch.p, 0, 256 + 64 * 256, e->stream);
         kstat = e->d_scratch.as<unsigned long long>();
     }
     static const bool pipe = [] { const char *v = getenv("HVS_K3_PIPE"); return !(v && v[0] == '0'); }();   // default: pipelined, unrolled stage scan
@@ -784,14 +826,26 @@ cudaError_t launch_tile_tensor(hvs_engine *e, const float *queries_dev, const QS
                                           ix.xb[0].as<unsigned char>(), ix.xb[1].as<unsigned char>(), ix.xnorm_max, ix.img_scale,
                                           e->d_pool.as<uint64_t>() + (size_t)e->pool_slot * e->sm_count * QT_TENSOR * POOL, cand_dev, cand_cnt_dev, gthr_dev, e->d_gbest.as<uint32_t>(),
                                           e->d_glock.as<uint32_t>() + e->stats.m, e->d_glock.as<uint32_t>() + 2 * (size_t)e->stats.m,
-                                          e->d_glock.as<uint32_t>(), flags_dev, dbg, kstat);
+                                          e->d_glock.as<uint32_t>(), flags_dev, e->d_work_counter.as<uint32_t>() + e->work_slot, dbg, kstat);
+    ++e->work_slot;
     if (kstat) {
-        unsigned long long h[20];
+        unsigned long long h[32 + 8 * 256];
         cudaStreamSynchronize(e->stream);
         cudaMemcpy(h, kstat, sizeof h, cudaMemcpyDeviceToHost);
+        {   // the three slowest CTAs and the fastest one
+            int idx[256];
+            for (uint32_t i = 0; i < grid && i < 256; ++i) idx[i] = (int)i;
+            std::sort(idx, idx + (grid < 256 ? grid : 256), [&](int a, int b) { return h[32 + 8 * a] > h[32 + 8 * b]; });
+            for (uint32_t k = 0; k < grid && k < 256; ++k) {
+                if (k >= 3 && k != grid - 1 && k != grid / 2) continue;
+                const unsigned long long *r = h + 32 + 8 * idx[k];
+                fprintf(stderr, "K3 CTA rank %u (block %d): total %.2f Mcycles, items %llu, scan %.2f (compact %.2f, n=%llu), wait_tfull %.2f, item_end %.2f, barrier %.2f\n",
+                        k, idx[k], r[0] / 1e6, r[1], r[2] / 1e6, r[3] / 1e6, r[4], r[5] / 1e6, r[6] / 1e6, r[7] / 1e6);
+            }
+        }
         const double ew = (double)h[8], mw = (double)h[12];
-        fprintf(stderr, "K3 hits: 32-column scans/warp %.0f, with a hit in the warp %.1f %%, lane hits per scan %.3f (with no threshold yet %.3f)\n",
-                h[16] / ew, 100.0 * h[17] / (double)(h[16] ? h[16] : 1), h[18] / (double)(h[16] ? h[16] : 1), h[19] / (double)(h[16] ? h[16] : 1));
+        fprintf(stderr, "K3 hits: 32-column scans/warp %.0f, with a hit in the warp %.1f %%, lane hits per scan %.3f (with no threshold yet %.3f); slowest CTA %.2f Mcycles\n",
+                h[16] / ew, 100.0 * h[17] / (double)(h[16] ? h[16] : 1), h[18] / (double)(h[16] ? h[16] : 1), h[19] / (double)(h[16] ? h[16] : 1), h[20] / 1e6);
         fprintf(stderr, "K3 stats per epilogue warp (Mcycles): total %.2f  wait_tfull %.2f  scan %.2f  (of which compact %.2f, n=%.1f)  item_end %.2f (merge_global %.2f)  A-build %.2f  barrier %.2f | survivors/warp %.0f | MMA warp: total %.2f wait_full %.2f wait_tempty %.2f\n",
                 h[0] / ew / 1e6, h[1] / ew / 1e6, h[2] / ew / 1e6, h[3] / ew / 1e6, h[6] / ew, h[4] / ew / 1e6, h[13] / ew / 1e6, h[14] / ew / 1e6, h[5] / ew / 1e6, h[7] / ew,
                 h[9] / mw / 1e6, h[10] / mw / 1e6, h[11] / mw / 1e6);
