@@ -165,6 +165,14 @@ HVS_API int hvs_merge_partials_device(hvs_engine *e, const float *queries_dev, u
  */
 HVS_API int hvs_rescore(hvs_engine *e, const float *queries_host, uint32_t m, const uint32_t *ids_host, float *out_dist_host);
 
+/*
+ * Solve + the `.dist` side file in one call (src/test.cpp:85 followed by src/test.cpp:97-110, which copies the
+ * 100 result rows of every query back into nested vectors only to hand them to SaveKNNFull): ids as hvs_solve,
+ * out_dist_host[i][k] = the reference's calc_dist (include/io.h:38-48) between query i and row out_ids[i][k],
+ * computed on the device from the rows already resident there.  Host pointers; m x 100 each.
+ */
+HVS_API int hvs_solve_full(hvs_engine *e, const float *queries_host, uint32_t m, uint32_t *out_ids_host, float *out_dist_host);
+
 HVS_API int hvs_get_stats(const hvs_engine *e, hvs_stats *out);
 
 /* Runs `iters` launches of an FFMA-only microkernel on the engine's device and returns the best

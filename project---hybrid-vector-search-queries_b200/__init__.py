@@ -36,7 +36,7 @@ HVS_OK, HVS_ERR_INVALID, HVS_ERR_NO_DEVICE, HVS_ERR_CUDA, HVS_ERR_STATE, HVS_ERR
 ABI_SYMBOLS = (
     "hvs_abi_version", "hvs_last_error", "hvs_create", "hvs_destroy", "hvs_index_build", "hvs_index_build_device",
     "hvs_index_build_rows", "hvs_index_build_from_file",
-    "hvs_solve", "hvs_solve_device", "hvs_solve_partial_device", "hvs_merge_partials_device", "hvs_rescore",
+    "hvs_solve", "hvs_solve_full", "hvs_solve_device", "hvs_solve_partial_device", "hvs_merge_partials_device", "hvs_rescore",
     "hvs_get_stats", "hvs_measure_ffma_peak", "hvs_plan_dryrun",
 )
 
@@ -110,6 +110,8 @@ def lib():
         L.hvs_merge_partials_device.argtypes = [vp, vp, u32, u32, vp, vp, vp, vp, u32, vp]
         L.hvs_rescore.restype = i32
         L.hvs_rescore.argtypes = [vp, vp, u32, vp, vp]
+        L.hvs_solve_full.restype = i32
+        L.hvs_solve_full.argtypes = [vp, vp, u32, vp, vp]
         L.hvs_get_stats.restype = i32
         L.hvs_get_stats.argtypes = [vp, C.POINTER(Stats)]
         L.hvs_measure_ffma_peak.restype = i32
@@ -193,6 +195,15 @@ class Engine:
         self._ck(lib().hvs_solve(self._h, q.ctypes.data, m, out.ctypes.data))
         return out
 
+    def solve_full(self, queries) -> tuple[np.ndarray, np.ndarray]:
+        """ids as solve(), plus the distances SaveKNNFull would write for them (include/io.h:50-78), one call."""
+        q = _host_f32(queries, QROW)
+        m = q.shape[0]
+        ids = np.empty((m, K), np.uint32)
+        dist = np.empty((m, K), np.float32)
+        self._ck(lib().hvs_solve_full(self._h, q.ctypes.data, m, ids.ctypes.data, dist.ctypes.data))
+        return ids, dist
+
     def solve_device(self, queries_dev, out_dev) -> None:
         m = queries_dev.shape[0]
         self._ck(lib().hvs_solve_device(self._h, _dev_ptr(queries_dev, "float32", m * QROW), m,
@@ -264,6 +275,41 @@ def save_knn_dist(dist, path: str) -> None:
     with open(path, "wb") as f:
         np.uint32(a.shape[0]).tofile(f)
         a.tofile(f)
+
+
+def read_knn_dist(path: str) -> np.ndarray:
+    """include/io.h ReadBinFull as src/compare_data.cpp uses it: uint32 M, then M x 100 float32.  Unlike the
+    reference (whose comparer reports "the same" for two missing files) a short or missing file is an error."""
+    size = os.path.getsize(path)
+    with open(path, "rb") as f:
+        m = int(np.fromfile(f, np.uint32, 1)[0])
+        if size != 4 + 4 * K * m:
+            raise ValueError(f"{path}: header says {m} queries, file holds {size} bytes (expected {4 + 4 * K * m})")
+        return np.fromfile(f, np.float32, m * K).reshape(m, K)
+
+
+def compare_dist(a: np.ndarray, b: np.ndarray, error_delta: float = 0.002) -> dict:
+    """src/compare_data.cpp:8-84 on two M x 100 distance tables: position-wise |a - b| in double; a difference
+    >= error_delta (src/compare_data.cpp:5) is an error.  Returns the counts and the verdict line it would print."""
+    a = np.asarray(a, np.float32)
+    b = np.asarray(b, np.float32)
+    if a.shape != b.shape:
+        return {"ok": False, "errors": -1, "max_error": float("nan"),
+                "verdict": f"Datasets have different number of queries! {a.shape[0]}, {b.shape[0]}"}
+    diff = np.abs(a.astype(np.float64) - b.astype(np.float64))
+    errs = int(np.count_nonzero(~(diff < error_delta)))     # NaN counts as an error
+    mx = float(diff.max()) if diff.size else 0.0
+    if errs == 0 and mx == 0.0:
+        verdict = "Datasets are the same!"
+    elif errs == 0:
+        verdict = "Datasets are similar under error delta!"
+    else:
+        verdict = f"ERROR: Found a total of {errs} differences!"
+    return {"ok": errs == 0, "errors": errs, "max_error": mx, "verdict": verdict}
+
+
+def compare_dist_files(a_path: str, b_path: str, error_delta: float = 0.002) -> dict:
+    return compare_dist(read_knn_dist(a_path), read_knn_dist(b_path), error_delta)
 
 
 def plan_dryrun(arena, begin, end, mode: int = MODE_EXACT, max_items: int = 1 << 20):

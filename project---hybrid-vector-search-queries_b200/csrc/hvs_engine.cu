@@ -366,6 +366,34 @@ extern "C" int hvs_solve(hvs_engine *e, const float *queries_host, uint32_t m, u
     return HVS_OK;
 }
 
+extern "C" int hvs_solve_full(hvs_engine *e, const float *queries_host, uint32_t m, uint32_t *out_ids_host, float *out_dist_host)
+{
+    int rc = check_solve_args(e, queries_host, m, out_ids_host);
+    if (rc) return rc;
+    if (m && !out_dist_host) EFAIL(HVS_ERR_INVALID, "hvs_solve_full: NULL buffer");
+    if (!m) return HVS_OK;
+    auto t0 = std::chrono::steady_clock::now();
+    cudaStream_t s = e->stream;
+    ECUDA(e->d_queries.ensure((size_t)m * QROW * 4));
+    ECUDA(e->d_out.ensure((size_t)m * K * 4));
+    ECUDA(e->d_rescore_out.ensure((size_t)m * K * 4));
+    cudaEventRecord(e->ev[0], s);
+    ECUDA(cudaMemcpyAsync(e->d_queries.p, queries_host, (size_t)m * QROW * 4, cudaMemcpyHostToDevice, s));
+    cudaEventRecord(e->ev[1], s);
+    rc = solve_impl(e, e->d_queries.as<float>(), m, false, e->d_out.as<uint32_t>(), nullptr, nullptr);
+    if (rc) return rc;
+    ECUDA(launch_rescore(e, e->d_queries.as<float>(), m, e->d_out.as<uint32_t>(), e->d_rescore_out.as<float>(), nullptr));
+    cudaEventRecord(e->ev[10], s);
+    ECUDA(cudaMemcpyAsync(out_ids_host, e->d_out.p, (size_t)m * K * 4, cudaMemcpyDeviceToHost, s));
+    ECUDA(cudaMemcpyAsync(out_dist_host, e->d_rescore_out.p, (size_t)m * K * 4, cudaMemcpyDeviceToHost, s));
+    cudaEventRecord(e->ev[11], s);
+    ECUDA(cudaStreamSynchronize(s));
+    e->stats.ms_h2d = ev_ms(e->ev[0], e->ev[1]);
+    e->stats.ms_d2h = ev_ms(e->ev[10], e->ev[11]);
+    e->stats.ms_solve_wall = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return HVS_OK;
+}
+
 extern "C" int hvs_solve_partial_device(hvs_engine *e, const float *queries_dev, uint32_t m, float *out_dist_dev,
                                         uint32_t *out_ids_dev, uint32_t *out_count_dev)
 {

@@ -308,3 +308,24 @@ def test_index_build_from_file_and_rows(H, oracle, check, datagen, tmp_path):
     with H.Engine() as e:
         with pytest.raises(H.HvsError):
             e.index_build_from_file(bpath)
+
+
+def test_solve_full_dist_side_file(H, oracle, check, datagen, tmp_path):
+    """hvs_solve_full = solve + SaveKNNFull (include/io.h:50-78) in one call: ids equal hvs_solve's, the distances
+    are the reference's calc_dist numbers (pad rows included), and the `.dist` file compares as
+    src/compare_data.cpp would against one written from the oracle's distances."""
+    d = datagen.gen_data(30_000, 31, ncat=40)
+    q = np.concatenate([datagen.gen_queries(200, 32, ncat=40), datagen.gen_queries(56, 33, ncat=40, types=(3,), range_width=0.02)])
+    with H.Engine(mode=H.MODE_AUTO) as e:
+        e.index_build(d)
+        ids = e.solve(q)
+        ids2, dist = e.solve_full(q)
+    assert np.array_equal(ids, ids2)
+    ref_dist = oracle.rescore(d, q, ids)
+    assert np.array_equal(dist.view(np.uint32), ref_dist.view(np.uint32))
+    a, b = str(tmp_path / "a.bin.dist"), str(tmp_path / "b.bin.dist")
+    H.save_knn_dist(dist, a)
+    H.save_knn_dist(ref_dist, b)
+    v = H.compare_dist_files(a, b)
+    assert v["ok"] and v["verdict"] == "Datasets are the same!" and v["max_error"] == 0.0
+    assert H.read_knn_dist(a).shape == (len(q), 100)

@@ -80,3 +80,25 @@ def test_planner_rejects_bad_slices(H):
         H.plan_dryrun([0], [5], [1])
     kind, items, pc = H.plan_dryrun(np.zeros(0), np.zeros(0), np.zeros(0))
     assert len(kind) == 0 and len(items) == 0 and pc == 0
+
+
+def test_compare_dist_mirrors_reference_checker(H, tmp_path):
+    """src/compare_data.cpp: |a-b| >= 0.002 is an error; identical tables are 'the same'; files must be whole."""
+    import numpy as np
+    import pytest
+    a = np.linspace(1.0, 5000.0, 3 * 100, dtype=np.float32).reshape(3, 100)
+    assert H.compare_dist(a, a)["verdict"] == "Datasets are the same!"
+    b = a.copy(); b[1, 7] += np.float32(0.0009765625)
+    v = H.compare_dist(a, b)
+    assert v["ok"] and v["verdict"] == "Datasets are similar under error delta!" and 0 < v["max_error"] < 0.002
+    c = a.copy(); c[2, 99] += np.float32(0.5); c[0, 0] = np.nan
+    v = H.compare_dist(a, c)
+    assert not v["ok"] and v["errors"] == 2 and v["verdict"].startswith("ERROR: Found a total of 2")
+    assert not H.compare_dist(a, a[:2])["ok"]
+    p = str(tmp_path / "x.dist")
+    H.save_knn_dist(a, p)
+    assert np.array_equal(H.read_knn_dist(p), a)
+    with open(p, "r+b") as f:
+        f.truncate(4 + 4 * 100 * 2)            # the reference's comparer would call two short files "the same"
+    with pytest.raises(ValueError):
+        H.read_knn_dist(p)
