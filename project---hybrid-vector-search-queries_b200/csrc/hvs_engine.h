@@ -101,7 +101,7 @@ struct Plan {
     // scratch kept between solves (fresh multi-megabyte vectors cost more in page faults than the planning)
     struct Local { std::vector<TileItem> items; std::vector<uint32_t> item_q, cstart, cur, fill; uint64_t pairs_computed = 0; };
     std::vector<Local> locals;
-    std::vector<uint64_t> sort_keys[2];
+    std::vector<std::pair<uint64_t, uint32_t>> sort_keys[2];   // (begin << 32 | end, query) of the tile queries of an arena
     std::vector<uint32_t> order[2], nlist, qpos;
     std::vector<uint8_t> is_tile;
     // incremental planning (plan_begin / plan_group / plan_finish): the sweep of group g runs on the GPU while

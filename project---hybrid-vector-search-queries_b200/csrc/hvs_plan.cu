@@ -120,6 +120,7 @@ void plan_begin(const QSlice *sl, uint32_t m, const PlanParams &pp, Plan &P)
     auto T0 = std::chrono::steady_clock::now();
     auto lap = [&](const char *what) { if (dbg) { auto t = std::chrono::steady_clock::now(); fprintf(stderr, "  plan %-14s %.2f ms\n", what, std::chrono::duration<double, std::milli>(t - T0).count()); T0 = t; } };
     P.reset();
+    lap("reset");
     const bool tensor = pp.tensor_available && (pp.mode == HVS_MODE_AUTO || pp.mode == HVS_MODE_TENSOR);
     const uint32_t BQ = tensor ? (uint32_t)QT_TENSOR : (uint32_t)QT;
     std::vector<uint8_t> &is_tile = P.is_tile;
@@ -159,6 +160,7 @@ void plan_begin(const QSlice *sl, uint32_t m, const PlanParams &pp, Plan &P)
                 }
         }
     }
+    lap("depth");
     for (uint32_t i = 0; i < m; ++i)
         if (!is_tile[i]) { P.direct_q.push_back(i); P.pairs_computed += sl[i].end - sl[i].begin; }
     // direct queries: neighbours in an arena share L2 lines.  A counting sort on (arena, begin >> 12) is all the
@@ -191,6 +193,7 @@ void plan_begin(const QSlice *sl, uint32_t m, const PlanParams &pp, Plan &P)
     if (R > (1u << 22)) R = 1u << 22;
     P.R = R;
 
+    lap("chunking");
     std::vector<uint32_t> *order = P.order;
     uint64_t incid = 0;
     P.nthreads = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 8u);
@@ -205,6 +208,7 @@ void plan_begin(const QSlice *sl, uint32_t m, const PlanParams &pp, Plan &P)
         }
     P.incid = incid;
     if (incid < 65536) P.nthreads = 1;
+    lap("collect");
     // tile queries of each arena ordered by (begin, end, index): each chunk's batches then group queries
     // with similar slices, which keeps the union of rows an item sweeps tight
     plan_parallel(P.nthreads, 2, [&](size_t a) {
@@ -214,12 +218,25 @@ void plan_begin(const QSlice *sl, uint32_t m, const PlanParams &pp, Plan &P)
         for (size_t k = 1; k < ord.size() && same; ++k)
             same = sl[ord[k]].begin == sl[ord[0]].begin && sl[ord[k]].end == sl[ord[0]].end;
         if (same) return;
-        std::sort(ord.begin(), ord.end(), [&](uint32_t x, uint32_t y) {
-            if (sl[x].begin != sl[y].begin) return sl[x].begin < sl[y].begin;
-            if (sl[x].end != sl[y].end) return sl[x].end < sl[y].end;
-            return x < y;
-        });
+        // sort (begin, end, index) as plain integers: no slice look-ups inside the comparator
+        std::vector<std::pair<uint64_t, uint32_t>> &keys = P.sort_keys[a];
+        keys.resize(ord.size());
+        for (size_t k = 0; k < ord.size(); ++k) keys[k] = {((uint64_t)sl[ord[k]].begin << 32) | sl[ord[k]].end, ord[k]};
+        // stable LSD radix sort on the 64-bit key (queries were collected in index order, so ties stay in index order)
+        std::vector<std::pair<uint64_t, uint32_t>> tmp(keys.size());
+        uint64_t all_or = 0, all_and = ~0ull;
+        for (const auto &kv : keys) { all_or |= kv.first; all_and &= kv.first; }
+        for (int shift = 0; shift < 64; shift += 11) {
+            if ((((all_or ^ all_and) >> shift) & 0x7ffull) == 0) continue;       // this digit is the same everywhere
+            uint32_t hist[2049] = {0};
+            for (const auto &kv : keys) ++hist[((kv.first >> shift) & 0x7ffull) + 1];
+            for (int d = 0; d < 2048; ++d) hist[d + 1] += hist[d];
+            for (const auto &kv : keys) tmp[hist[(kv.first >> shift) & 0x7ffull]++] = kv;
+            keys.swap(tmp);
+        }
+        for (size_t k = 0; k < ord.size(); ++k) ord[k] = keys[k].second;
     });
+    lap("sort");
     // tasks = (arena, block of chunks); the (C,T) arena first: its slices are short, so the GPU gets work early
     for (int a = 1; a >= 0; --a) {
         if (order[a].empty()) continue;
@@ -227,11 +244,24 @@ void plan_begin(const QSlice *sl, uint32_t m, const PlanParams &pp, Plan &P)
         const uint32_t per = std::max(1u, (nchunk + 7) / 8);
         for (uint32_t c = 0; c < nchunk; c += per) P.tasks.push_back({(uint32_t)a, c, std::min(nchunk, c + per), 0});
     }
-    for (auto &tk : P.tasks)
-        for (uint32_t i : order[tk.arena]) {
-            const uint32_t lo = std::max(sl[i].begin / R, tk.c0), hi = std::min((sl[i].end - 1) / R + 1, tk.c1);
-            if (hi > lo) tk.incid += hi - lo;
-        }
+    {   // incidences per task: every query adds its chunk range to the (few) tasks it overlaps
+        size_t tbase[2] = {0, 0};
+        uint32_t tper[2] = {1, 1};
+        for (size_t ti = 0; ti < P.tasks.size(); ++ti)
+            if (ti == 0 || P.tasks[ti].arena != P.tasks[ti - 1].arena) {
+                tbase[P.tasks[ti].arena] = ti;
+                tper[P.tasks[ti].arena] = P.tasks[ti].c1 - P.tasks[ti].c0;      // every task but the last of an arena spans `per` chunks
+            }
+        for (uint32_t a = 0; a < 2; ++a)
+            for (uint32_t i : order[a]) {
+                const uint32_t lo = sl[i].begin / R, hi = (sl[i].end - 1) / R + 1;
+                for (uint32_t t = lo / tper[a]; t <= (hi - 1) / tper[a]; ++t) {
+                    Plan::Task &tk = P.tasks[tbase[a] + t];
+                    const uint32_t l2 = std::max(lo, tk.c0), h2 = std::min(hi, tk.c1);
+                    if (h2 > l2) tk.incid += h2 - l2;
+                }
+            }
+    }
     // groups: ~20 % / 40 % / 40 % of the incidences, so that little planning stands before the first launch
     const int ng = incid >= 200000 && P.tasks.size() >= 3 ? 3 : 1;
     const double cutf[3] = {ng == 1 ? 1.0 : 0.2, 0.6, 1.0};
