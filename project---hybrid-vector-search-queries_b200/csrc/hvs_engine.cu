@@ -172,6 +172,8 @@ static int solve_impl(hvs_engine *e, const float *q_dev, uint32_t m, bool partia
     PlanParams pp;
     pp.mode = e->mode;
     pp.tensor_available = tensor_path_available() && e->index.xb[0].p != nullptr;
+    static const long long min_pairs_env = [] { const char *v = getenv("HVS_MIN_TILE_PAIRS"); return v ? atoll(v) : -1ll; }();
+    if (min_pairs_env >= 0) pp.min_tile_pairs = (uint64_t)min_pairs_env;   // tests set 0: tile kernels run on tiny inputs too
     Plan &P = e->plan;
     const QSlice *h_sl = e->h_slices.as<QSlice>();
     plan_begin(h_sl, m, pp, P);                      // classify; tile queries are cut into groups of chunk blocks

@@ -128,6 +128,8 @@ struct PlanParams {
     uint32_t min_tile_len = 1024;         // shorter slices always take the direct scan
     double direct_cost_ratio = 12.0;      // FFMA tile pair-slot vs direct pair throughput ratio
     double tensor_min_depth = 0.75;       // tensor items: average queries per row needed (the sweep is bandwidth-, not slot-priced)
+    uint64_t min_tile_pairs = 4000000;    // below this many (query,row) pairs a tile sweep's fixed cost (~0.5 ms: persistent launch, operand
+                                          // build, finalize) exceeds the direct scan of all of them: everything goes direct
     bool tensor_available = false;
 };
 

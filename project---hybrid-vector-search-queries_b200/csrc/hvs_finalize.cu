@@ -46,33 +46,42 @@ k_finalize(const float *__restrict__ queries, const QSlice *__restrict__ slices,
     const float margin = tensor_sx > 0.f ? margin_tensor(sl.qnorm, xnorm_max, tensor_sx) * tensor_sx * tensor_sx
                                          : margin_ffma(sl.qnorm, xnorm_max);
 
-    // phase 1: the rows whose approximate score is within the margin of the global 100-th best
-    // Four lists per round, one warp each: the list lengths of a round are fetched together, so a query with
-    // 77 lists pays ~20 dependent round trips to L2 instead of 77.
+    // phase 1: the rows whose approximate score is within the margin of the global 100-th best.
+    // A query swept in 77 chunks has 77 short lists.  Their ids and lengths are fetched LCH at a time (one pair of
+    // dependent round trips to L2 for the lot), then the lists are read in batches whose lengths add up to at most
+    // P1ROUND entries -- usually ONE batch for all lists -- one warp per list, so the whole phase costs a handful of
+    // dependent round trips instead of three per list.
     const uint32_t l0 = qoff[blockIdx.x], l1 = qoff[blockIdx.x + 1];
-    constexpr uint32_t LPR = FT / 32;
-    __shared__ uint32_t s_list[LPR], s_len[LPR];
+    constexpr uint32_t LCH = 128, P1ROUND = 1024;                 // P1ROUND >= KOUT: a batch always holds at least one list
+    __shared__ uint32_t s_list[LCH], s_len[LCH];
     const uint32_t warp = tid >> 5, lane = tid & 31;
-    for (uint32_t lb = l0; lb < l1; lb += LPR) {
-        if ((uint32_t)tid < LPR) {
-            uint32_t list = 0, c = 0;
-            if (lb + tid < l1) { list = qlists[lb + tid]; c = min(cand_cnt[list], (uint32_t)KOUT); }
-            s_list[tid] = list; s_len[tid] = c;
+    for (uint32_t lb = l0; lb < l1; lb += LCH) {
+        const uint32_t nl = min(LCH, l1 - lb);
+        for (uint32_t i = tid; i < nl; i += FT) {
+            const uint32_t list = qlists[lb + i];
+            s_list[i] = list;
+            s_len[i] = min(cand_cnt[list], (uint32_t)KOUT);
         }
         __syncthreads();
-        {
-            const uint32_t list = s_list[warp], c = s_len[warp];
-            for (uint32_t e = lane; e < c; e += 32) {
-                const uint64_t k = cand[(size_t)list * KOUT + e];
-                const float s = okey_inv((uint32_t)(k >> 32));
-                if (s < S.p1.thr) {
-                    const uint32_t slot = atomicAdd(&S.p1.cnt, 1u);
-                    S.p1.cand[slot] = k;                     // cnt <= P1CAP - LPR * KOUT before every round
+        for (uint32_t i0 = 0; i0 < nl;) {
+            uint32_t i1 = i0, sum = 0;                            // every thread walks the same lengths: uniform
+            while (i1 < nl && sum + s_len[i1] <= P1ROUND) sum += s_len[i1++];
+            for (uint32_t i = i0 + warp; i < i1; i += FT / 32) {
+                const uint32_t list = s_list[i], c = s_len[i];
+                for (uint32_t e = lane; e < c; e += 32) {
+                    const uint64_t k = cand[(size_t)list * KOUT + e];
+                    const float sc = okey_inv((uint32_t)(k >> 32));
+                    if (sc < S.p1.thr) {
+                        const uint32_t slot = atomicAdd(&S.p1.cnt, 1u);
+                        S.p1.cand[slot] = k;                     // cnt <= P1CAP - P1ROUND before every batch
+                    }
                 }
             }
+            __syncthreads();
+            if (S.p1.cnt > (uint32_t)(P1CAP - P1ROUND)) S.p1.compact(tid, FT, margin, P1KEEP);
+            i0 = i1;
         }
-        __syncthreads();
-        if (S.p1.cnt > (uint32_t)(P1CAP - LPR * KOUT)) S.p1.compact(tid, FT, margin, P1KEEP);
+        __syncthreads();                                          // s_list / s_len are rewritten by the next chunk
     }
     S.p1.compact(tid, FT, margin, P1KEEP);
     if (S.p1.overflow && tid == 0) flags[q] = 1u;            // K4 re-solves this query

@@ -160,6 +160,11 @@ void plan_begin(const QSlice *sl, uint32_t m, const PlanParams &pp, Plan &P)
                 }
         }
     }
+    if (tile_qrows && tile_qrows < pp.min_tile_pairs && pp.mode != HVS_MODE_TENSOR) {   // tiny job: not worth a sweep
+        std::fill(is_tile.begin(), is_tile.end(), (uint8_t)0);
+        tile_qrows = 0;
+        P.pairs_tile = 0;
+    }
     lap("depth");
     for (uint32_t i = 0; i < m; ++i)
         if (!is_tile[i]) { P.direct_q.push_back(i); P.pairs_computed += sl[i].end - sl[i].begin; }

@@ -102,3 +102,15 @@ def test_compare_dist_mirrors_reference_checker(H, tmp_path):
         f.truncate(4 + 4 * 100 * 2)            # the reference's comparer would call two short files "the same"
     with pytest.raises(ValueError):
         H.read_knn_dist(p)
+
+
+def test_planner_tiny_job_goes_direct(H):
+    """BASELINE.json configs[0] sized job (100 queries x 10^4 rows = 10^6 pairs): a tile sweep's fixed cost would
+    dominate, so every query takes the direct scan; the same shape 100x larger is swept in tiles."""
+    m = 100
+    arena = np.zeros(m, np.uint32); begin = np.zeros(m, np.uint32)
+    for mode in (H.MODE_EXACT, H.MODE_AUTO):
+        kind, items, pc = H.plan_dryrun(arena, begin, np.full(m, 10_000, np.uint32), mode)
+        assert not kind.any() and len(items) == 0 and pc == m * 10_000
+        kind, items, _ = H.plan_dryrun(arena, begin, np.full(m, 1_000_000, np.uint32), mode)
+        assert kind.all() and len(items) > 0
