@@ -78,12 +78,12 @@ k_finalize(const float *__restrict__ queries, const QSlice *__restrict__ slices,
                 }
             }
             __syncthreads();
-            if (S.p1.cnt > (uint32_t)(P1CAP - P1ROUND)) S.p1.compact(tid, FT, margin, P1KEEP);
+            if (S.p1.cnt > (uint32_t)(P1CAP - P1ROUND)) S.p1.compact_select<FT>(tid, margin, P1KEEP);
             i0 = i1;
         }
         __syncthreads();                                          // s_list / s_len are rewritten by the next chunk
     }
-    S.p1.compact(tid, FT, margin, P1KEEP);
+    S.p1.compact_select<FT>(tid, margin, P1KEEP);
     if (S.p1.overflow && tid == 0) flags[q] = 1u;            // K4 re-solves this query
 
     // phase 2: the reference's arithmetic on the survivors

@@ -129,25 +129,6 @@ struct QState {
     uint32_t cnt, qlo, qhi, qid;
 };
 
-// Next probe of the rank search shared by compact_warp and merge_global: a score v between the bracket ends
-// (#{<= klo} = clo < K <= chi = #{<= khi}).  The survivors sit in the lower tail of the score distribution, where the
-// count grows roughly exponentially with the score, so the probe interpolates log(count) linearly -- in the FLOAT
-// domain (order-preserving keys are very non-linear around zero) -- and every third step bisects the key interval,
-// which bounds the worst case.  Measured on pools of 192..480 tail scores: ~3 probes instead of 9-18 with linear
-// interpolation on the keys.
-__device__ __forceinline__ uint32_t select_probe(uint32_t klo, uint32_t khi, uint32_t clo, uint32_t chi, int it)
-{
-    uint32_t mid;
-    if (it % 3 == 2) mid = klo + ((khi - klo) >> 1);
-    else {
-        const float flo = okey_inv(klo), fhi = okey_inv(khi);
-        const float a = __logf(fmaxf((float)clo, 0.5f)), b = __logf((float)chi);
-        const float t = (__logf((float)(K + 4)) - a) / fmaxf(b - a, 1e-6f);
-        mid = okey(flo + (fhi - flo) * fminf(fmaxf(t, 0.f), 1.f));
-    }
-    return min(max(mid, klo + 1u), khi - 1u);
-}
-
 // Pools are transposed: entry i of the query owned by lane l lives at pool_warp[i * 32 + l], so that the
 // 32 lanes of a warp walk their 32 pools in lock step with fully coalesced loads.
 //

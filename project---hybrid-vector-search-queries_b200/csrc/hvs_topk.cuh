@@ -62,6 +62,25 @@ __device__ __forceinline__ float okey_inv(uint32_t k)
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
+// Next probe of the rank search shared by K3's compact_warp / merge_global and K5's compact_select: a score v between the bracket ends
+// (#{<= klo} = clo < K <= chi = #{<= khi}).  The survivors sit in the lower tail of the score distribution, where the
+// count grows roughly exponentially with the score, so the probe interpolates log(count) linearly -- in the FLOAT
+// domain (order-preserving keys are very non-linear around zero) -- and every third step bisects the key interval,
+// which bounds the worst case.  Measured on pools of 192..480 tail scores: ~3 probes instead of 9-18 with linear
+// interpolation on the keys.
+__device__ __forceinline__ uint32_t select_probe(uint32_t klo, uint32_t khi, uint32_t clo, uint32_t chi, int it)
+{
+    uint32_t mid;
+    if (it % 3 == 2) mid = klo + ((khi - klo) >> 1);
+    else {
+        const float flo = okey_inv(klo), fhi = okey_inv(khi);
+        const float a = __logf(fmaxf((float)clo, 0.5f)), b = __logf((float)chi);
+        const float t = (__logf((float)(K + 4)) - a) / fmaxf(b - a, 1e-6f);
+        mid = okey(flo + (fhi - flo) * fminf(fmaxf(t, 0.f), 1.f));
+    }
+    return min(max(mid, klo + 1u), khi - 1u);
+}
+
 // Warp-cooperative merge of up to 32 new keys (lane i passes key i, KEY_INF when it has none) into a
 // sorted candidate list L[0..nl) in global memory (nl <= KOUT_), in place and without scratch:
 // the new keys are sorted across lanes with shuffles, every element's merged position is its own
@@ -212,6 +231,71 @@ struct TopBuf {
             if (tid == 0) { cnt = keep; thr = (margin > 0.f) ? nextafterf(lim, __int_as_float(0x7f800000)) : dk; }
         } else if (tid == 0) {
             cnt = c;
+        }
+        __syncthreads();
+    }
+    // Same contract as compact() for margin > 0, ORD keys and a block of NT threads -- without sorting: the entries
+    // go to registers, the block brackets a score v with K <= #{<= v} <= K + 8 by counting (select_probe: ~3-4
+    // probes, one barrier each), and writes back what is within `margin` of v.  K5 spent most of its time in the
+    // 55 barrier-separated steps of a 1024-key bitonic sort here; order was never needed, only the cut.
+    template <int NT>
+    __device__ __forceinline__ void compact_select(int tid, float margin, int keep_max)
+    {
+        static_assert(ORD, "scores of either sign");
+        constexpr int PER = (CAP + NT - 1) / NT;
+        __shared__ uint32_t s_lo, s_hi, s_cnt[3];
+        const int c = min((int)cnt, CAP);
+        if (c <= K) {                                                 // nothing to cut (cnt is block-uniform here)
+            if (tid == 0) cnt = c;
+            __syncthreads();
+            return;
+        }
+        uint64_t e[PER];
+        uint32_t lo = 0xffffffffu, hi = 0u;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            const int i = tid + j * NT;
+            e[j] = i < c ? cand[i] : KEY_INF;
+            if (i < c) { lo = min(lo, (uint32_t)(e[j] >> 32)); hi = max(hi, (uint32_t)(e[j] >> 32)); }
+        }
+        if (tid == 0) { s_lo = 0xffffffffu; s_hi = 0u; s_cnt[0] = s_cnt[1] = s_cnt[2] = 0u; }
+        __syncthreads();
+        lo = __reduce_min_sync(0xffffffffu, lo);
+        hi = __reduce_max_sync(0xffffffffu, hi);
+        if ((tid & 31) == 0) { atomicMin(&s_lo, lo); atomicMax(&s_hi, hi); }
+        __syncthreads();
+        uint32_t klo = s_lo, khi = s_hi, clo = 0u, chi = (uint32_t)c;   // #{<= klo} = clo < K <= chi = #{<= khi}
+        if (klo != khi) {
+            klo -= 1u;
+            for (int it = 0; it < 48 && khi - klo > 1u; ++it) {
+                const uint32_t mid = select_probe(klo, khi, clo, chi, it);
+                uint32_t n = 0;
+#pragma unroll
+                for (int j = 0; j < PER; ++j) n += (tid + j * NT < c && (uint32_t)(e[j] >> 32) <= mid) ? 1u : 0u;
+                n = __reduce_add_sync(0xffffffffu, n);
+                if ((tid & 31) == 0 && n) atomicAdd(&s_cnt[it % 3], n);
+                __syncthreads();
+                n = s_cnt[it % 3];
+                if (tid == 0) s_cnt[(it + 2) % 3] = 0u;                // used two probes from now: behind the next barrier
+                if (n >= (uint32_t)K) { khi = mid; chi = n; if (n <= (uint32_t)K + 8u) break; }
+                else { klo = mid; clo = n; }
+            }
+        }
+        const float lim = okey_inv(khi) + margin;
+        const uint32_t limk = okey(lim);
+        __syncthreads();
+        if (tid == 0) cnt = 0u;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < PER; ++j)
+            if (tid + j * NT < c && (uint32_t)(e[j] >> 32) <= limk) {
+                const uint32_t slot = atomicAdd(&cnt, 1u);
+                if (slot < (uint32_t)keep_max) cand[slot] = e[j];
+            }
+        __syncthreads();
+        if (tid == 0) {
+            if (cnt > (uint32_t)keep_max) { cnt = (uint32_t)keep_max; overflow = 1; }
+            thr = nextafterf(lim, __int_as_float(0x7f800000));
         }
         __syncthreads();
     }
