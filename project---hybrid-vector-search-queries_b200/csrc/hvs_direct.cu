@@ -77,7 +77,8 @@ cudaError_t launch_direct(hvs_engine *e, const float *queries_dev, const QSlice 
                           uint32_t nq, bool partial, uint32_t *out_ids, float *out_dist, uint32_t *out_count)
 {
     if (!nq) return cudaSuccess;
-    static bool attr_done = false;
+    static bool attr_done_dev[64] = {false};                  // the attribute is per device
+    bool &attr_done = attr_done_dev[e->device & 63];
     const int smem = (int)sizeof(DirectSmem);
     if (!attr_done) {
         cudaError_t c = cudaFuncSetAttribute(k_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

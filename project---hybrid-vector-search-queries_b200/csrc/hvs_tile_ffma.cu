@@ -265,7 +265,8 @@ cudaError_t launch_tile_ffma(hvs_engine *e, const float *queries_dev, const QSli
                              uint32_t *cand_cnt_dev, uint32_t *gthr_dev, uint32_t *flags_dev, float margin_scale)
 {
     if (!n_items) return cudaSuccess;
-    static bool attr_done = false;
+    static bool attr_done_dev[64] = {false};                  // the attribute is per device
+    bool &attr_done = attr_done_dev[e->device & 63];
     const int smem = (int)sizeof(TileSmem);
     if (!attr_done) {
         cudaError_t c = cudaFuncSetAttribute(k_tile_ffma, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

@@ -12,7 +12,8 @@
 // canonical K-major no-swizzle layout (8-row x 16-byte core matrices), so a stage of 128 rows is
 // one contiguous 28,672-byte block moved by ONE 1-D TMA bulk copy -- no tensor map, no swizzle.
 //
-// Persistent kernel, one CTA per SM, work items taken round-robin.  An item = up to 256 queries
+// Persistent kernel, one CTA per SM, work items handed out dynamically (one atomicAdd per item, longest
+// first).  An item = up to 256 queries
 // (two M=128 halves sharing every B stage) x a run of arena rows.  Warp roles: warp 0 TMA producer,
 // warp 1 / warp 10 MMA issuers of query half 0 / 1 (independent pipelines; warp 1 owns TMEM),
 // warps 2..9 epilogue (warp w reads TMEM lanes 32*(w%4)..; one thread = one query).  Four
@@ -24,16 +25,19 @@
 // and K5 re-ranks all survivors with the reference's fp32 arithmetic.  Survivors are appended to a
 // per-(CTA, query) pool in global memory (L2 resident, transposed so that the 32 lanes of a warp walk
 // their 32 pools with coalesced loads) by the thread that owns the query.  When a pool fills, all 32
-// queries of the warp are compacted together, lane-parallel: each lane searches (regula falsi on the
-// counting function) for a score with ~100 entries at or below it, keeps what is within the margin
-// of it and tightens its threshold -- no sorting.  At the end of an item every lane folds its pool
+// queries of the warp are compacted together, lane-parallel: each lane brackets (select_probe: log-count
+// interpolation on the counting function) a score with ~100 entries at or below it, keeps what is within
+// the margin of it and tightens its threshold -- no sorting; the warps of a query half compact together
+// (shared epoch), because they hand accumulators back together.  At the end of an item every lane folds its pool
 // into its query's GLOBAL list of best scores (all row chunks, per-query try-lock), so a CTA that
 // later sweeps another chunk of the slice starts with (nearly) the final threshold (`gthr`).
 //
 // Roofline: tensor pipe -- 2 x 7 MMAs (M128 N128 K16) = 896 tensor cycles per 128-row stage per SM;
-// the epilogue must read the 128 KB of fp32 accumulators of a stage out of TMEM (the measured limit
-// of this design: ~1000 cycles per stage per SM sub-partition pair); the B stream is 28,672 B per
-// stage per SM.  HVS_K3_STATS=1 prints the cycle budget per warp role.
+// the epilogue must read the 128 KB of fp32 accumulators of a stage out of TMEM, and while the tensor
+// core accumulates those reads take its TMEM port (measured: MMA + TMA alone 906 cycles per stage, with the
+// reads 1030; tcgen05.ld alone moves 750-980 B/clk/SM, tools/tmem_bw.cu); the B stream is 28,672 B per
+// stage per SM.  HVS_K3_STATS=1 prints the cycle budget per warp role, the hit statistics of the scan and
+// the slowest CTAs; DESIGN.md section 9 has the numbers.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -780,7 +784,8 @@ cudaError_t launch_tile_tensor(hvs_engine *e, const float *queries_dev, const QS
                                uint32_t *cand_cnt_dev, uint32_t *gthr_dev, uint32_t *flags_dev)
 {
     if (!n_items) return cudaSuccess;
-    static bool attr_done = false;
+    static bool attr_done_dev[64] = {false};                  // the attribute is per device (one engine per GPU, maybe several per process)
+    bool &attr_done = attr_done_dev[e->device & 63];
     const int smem = (int)sizeof(TensorSmem);
     if (!attr_done) {
         cudaError_t c = cudaFuncSetAttribute(k_tile_tensor<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

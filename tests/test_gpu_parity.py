@@ -329,3 +329,17 @@ def test_solve_full_dist_side_file(H, oracle, check, datagen, tmp_path):
     v = H.compare_dist_files(a, b)
     assert v["ok"] and v["verdict"] == "Datasets are the same!" and v["max_error"] == 0.0
     assert H.read_knn_dist(a).shape == (len(q), 100)
+
+
+@pytest.mark.parametrize("zipf,clusters,sigma", [(1.2, 0, 0.0), (0.0, 12, 0.25), (1.0, 40, 1.0)])
+def test_skewed_categories_and_clustered_vectors(H, oracle, check, datagen, zipf, clusters, sigma):
+    """SURVEY 8f-3 inputs: Zipf-skewed categories (huge and tiny slices side by side) and clustered vectors with
+    queries drawn near the data (distances concentrate, many near-ties inside a cluster: the hard case for the
+    candidate margins).  Same bar as everywhere: the reference's ids, bit-identical distances."""
+    n, m = 60_000, 320
+    d = datagen.gen_data(n, 41, ncat=30, zipf=zipf, clusters=clusters, cluster_sigma=sigma or 0.5)
+    q = datagen.gen_queries(m, 42, ncat=30, near=d if clusters else None, near_sigma=sigma or 0.5)
+    ref = oracle.vec_query(d, q, want_dist=False)
+    for tag, mode in modes(H):
+        ids, st, dd = solve(H, d, q, mode)
+        assert_parity(check, oracle, d, q, ref, ids, dd, f"zipf={zipf} clusters={clusters}/{tag}")
