@@ -283,6 +283,8 @@ void plan_begin(const QSlice *sl, uint32_t m, const PlanParams &pp, Plan &P)
 
 void plan_group(const QSlice *sl, Plan &P, size_t g, uint32_t &item_begin, uint32_t &item_end)
 {
+    static const bool dbg = getenv("HVS_PLAN_DEBUG") != nullptr;
+    const auto T0 = std::chrono::steady_clock::now();
     using Local = Plan::Local;
     const uint32_t R = P.R, BQ = P.BQ;
     const bool tensor = P.tensor;
@@ -358,6 +360,7 @@ void plan_group(const QSlice *sl, Plan &P, size_t g, uint32_t &item_begin, uint3
         P.n_lists += it.nq;
         if (it.kind) ++P.n_tensor; else ++P.n_ffma;
     }
+    if (dbg) fprintf(stderr, "  plan group %zu      %.2f ms (%u items)\n", g, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - T0).count(), item_end - item_begin);
 }
 
 void plan_finish(const QSlice *sl, uint32_t m, Plan &P)
