@@ -267,14 +267,22 @@ void plan_begin(const QSlice *sl, uint32_t m, const PlanParams &pp, Plan &P)
                 }
             }
     }
-    // groups: ~20 % / 40 % / 40 % of the incidences, so that little planning stands before the first launch
+    // groups: ~20 % / 40 % / 40 % of the incidences, so that little planning stands before the first launch; when the
+    // (C,T) arena's tasks are a small head of the list they form a group of their own -- planned in a fraction of a
+    // millisecond, it gives the GPU work while the host is still planning the T arena
     const int ng = incid >= 200000 && P.tasks.size() >= 3 ? 3 : 1;
     const double cutf[3] = {ng == 1 ? 1.0 : 0.2, 0.6, 1.0};
     uint64_t run = 0;
     int g = 0;
     for (size_t ti = 0; ti < P.tasks.size(); ++ti) {
         run += P.tasks[ti].incid;
-        if (g < ng - 1 && (double)run >= cutf[g] * (double)incid) { P.group_end.push_back((uint32_t)ti + 1); ++g; }
+        const bool last = ti + 1 == P.tasks.size();
+        if (ng > 1 && !last && P.group_end.empty() && P.tasks[ti + 1].arena != P.tasks[ti].arena &&
+            (double)run < cutf[0] * (double)incid && run > 0) {
+            P.group_end.push_back((uint32_t)ti + 1);                  // head group: the whole (C,T) arena
+            continue;
+        }
+        if (g < ng - 1 && !last && (double)run >= cutf[g] * (double)incid) { P.group_end.push_back((uint32_t)ti + 1); ++g; }
     }
     P.group_end.push_back((uint32_t)P.tasks.size());
     if (P.locals.size() < P.tasks.size()) P.locals.resize(P.tasks.size());
