@@ -64,6 +64,7 @@ constexpr int NTHR = 352;              // warp 0 TMA, warp 1 MMA issuer of query
 constexpr int POOL = TENSOR_POOL;     // survivor pool entries per query (global memory)
 constexpr uint32_t FULL = 0xffffffffu;
 constexpr int GB = TENSOR_GBEST;      // per-query global list of best scores over all finished chunks
+constexpr int SPARSE_LANES = 6;       // compaction: up to this many participating lanes are handled one query at a time by the whole warp
 
 static_assert(QT_TENSOR == 256, "two M=128 halves");
 static_assert(POOL == 512 && KOUT <= POOL - 32, "pool must take 32 more survivors after a compaction");
@@ -148,6 +149,73 @@ __device__ __noinline__ uint2 compact_warp(uint32_t cnt, float thr, float margin
     const bool part = valid && cnt >= (uint32_t)K;                    // lanes that take part
     const uint32_t maxc = __reduce_max_sync(FULL, part ? cnt : 0u);
     if (maxc == 0) return make_uint2(cnt, __float_as_uint(thr));
+    // Few lanes take part (queries whose slices start at different rows warm up one after the other: type-1/3 items,
+    // the first chunks of type-2 slices): the lane-parallel passes below would stream all 32 pools for them.  Instead
+    // the WARP takes one such query at a time: its <= 512 entries go to registers (16 per lane, one round trip), the
+    // rank is bracketed with warp-wide counts -- no further memory passes -- and the kept entries are written back.
+    const uint32_t pmask = __ballot_sync(FULL, part);
+    if (__popc(pmask) <= SPARSE_LANES) {
+        static_assert(POOL == 512, "16 entries per lane");
+        uint32_t my_cnt = cnt;
+        float my_thr = thr;
+        for (uint32_t mm = pmask; mm; mm &= mm - 1u) {
+            const int src = __ffs((int)mm) - 1;
+            const uint32_t c = __shfl_sync(FULL, cnt, src), q_src = __shfl_sync(FULL, qid, src);
+            const float thr_src = __shfl_sync(FULL, thr, src), margin_src = __shfl_sync(FULL, margin, src);
+            uint64_t e[16];
+            uint32_t klo = 0xffffffffu, khi = 0u;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const uint32_t idx = (uint32_t)lane + 32u * j;
+                e[j] = idx < c ? __ldcg(pool_warp + (size_t)32 * idx + src) : ~0ull;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if ((uint32_t)lane + 32u * j < c) { klo = min(klo, (uint32_t)(e[j] >> 32)); khi = max(khi, (uint32_t)(e[j] >> 32)); }
+            klo = __reduce_min_sync(FULL, klo);
+            khi = __reduce_max_sync(FULL, khi);
+            if (klo != khi) {                                         // #{<= klo} = clo < K <= chi = #{<= khi}
+                uint32_t clo = 0u, chi = c;
+                klo -= 1u;
+                for (int it = 0; it < 48 && khi - klo > 1u; ++it) {
+                    const uint32_t mid = select_probe(klo, khi, clo, chi, it);
+                    uint32_t n = 0;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) n += ((uint32_t)lane + 32u * j < c && (uint32_t)(e[j] >> 32) <= mid) ? 1u : 0u;
+                    n = __reduce_add_sync(FULL, n);
+                    if (n >= (uint32_t)K) { khi = mid; chi = n; if (n <= (uint32_t)K + 8u) break; }
+                    else { klo = mid; clo = n; }
+                }
+            }
+            const float lim = okey_inv(khi) + margin_src;
+            const uint32_t limk = okey(lim);
+            uint32_t kc = 0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) kc += ((uint32_t)lane + 32u * j < c && (uint32_t)(e[j] >> 32) <= limk) ? 1u : 0u;
+            uint32_t pos = kc;                                        // inclusive scan over the lanes
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL, pos, o); if (lane >= o) pos += v; }
+            uint32_t w = __shfl_sync(FULL, pos, 31);
+            pos -= kc;
+            __syncwarp();                                             // every lane holds its share: the pool may be rewritten
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if ((uint32_t)lane + 32u * j < c && (uint32_t)(e[j] >> 32) <= limk) {
+                    if (pos < keep_cap) pool_warp[(size_t)32 * pos + src] = e[j];
+                    ++pos;
+                }
+            if (w > keep_cap) {                                       // more rows inside the margin than a list may hold
+                if (flags && lane == 0) flags[q_src] = 1u;
+                w = keep_cap;
+            }
+            const float mine = nextafterf(lim, __int_as_float(0x7f800000));
+            const float theirs = okey_inv(ld_relaxed_u32(&gthr[q_src]));
+            if (lane == 0 && mine < theirs) atomicMin(&gthr[q_src], okey(mine));
+            if (lane == src) { my_cnt = w; my_thr = fminf(thr_src, fminf(mine, theirs)); }
+        }
+        __syncwarp();
+        return make_uint2(my_cnt, __float_as_uint(my_thr));
+    }
     const uint32_t *sc = reinterpret_cast<const uint32_t *>(pool_warp) + 2 * lane + 1;   // score word of entry i: sc[64 i]
     // First pass: range of the scores, and the count at a first probe -- the bound the previous compaction left
     // (thr - margin still has at least K entries at or below it; with no threshold yet the probe counts nothing).
