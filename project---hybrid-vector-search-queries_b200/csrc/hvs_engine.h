@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -110,6 +111,16 @@ struct Plan {
     std::vector<Task> tasks;
     std::vector<uint32_t> group_end;      // tasks [group_end[g-1], group_end[g]) form group g
     uint32_t R = 0, BQ = 0;
+    std::vector<uint32_t> bnd[2];         // chunk boundaries of each arena: chunk c = rows [bnd[c], bnd[c+1]); <= R rows each
+    std::vector<uint32_t> bnd_lut[2];     // non-uniform boundaries only: chunk that holds row (cell << 12)
+    bool uniform_chunks = true;           // boundaries are the multiples of R
+    uint32_t chunk_of(uint32_t a, uint32_t row) const   // the chunk that holds `row`
+    {
+        if (uniform_chunks) return row / R;
+        uint32_t c = bnd_lut[a][row >> 12];
+        while (row >= bnd[a][c + 1]) ++c;
+        return c;
+    }
     bool tensor = false;
     uint64_t incid = 0;                   // (chunk, query) incidences == candidate lists of the whole solve
     unsigned nthreads = 1;

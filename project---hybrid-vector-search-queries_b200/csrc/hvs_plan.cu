@@ -209,8 +209,56 @@ void plan_begin(const QSlice *sl, uint32_t m, const PlanParams &pp, Plan &P)
             const uint32_t a = sl[i].arena;
             order[a].push_back(i);
             maxend[a] = std::max(maxend[a], sl[i].end);
-            incid += (sl[i].end - 1) / R - sl[i].begin / R + 1;
         }
+    // Chunk boundaries.  Default: multiples of R.  HVS_ALIGN_CHUNKS=1 (experimental, not measured yet): a boundary moves
+    // back to the row at which the most tile queries' slices begin (at least 8), if that keeps the chunk above R/2 rows -- slices that
+    // start at a boundary (categories in the (C,T) arena) are then not cut in two a few rows later.
+    static const bool align_chunks = [] { const char *v = getenv("HVS_ALIGN_CHUNKS"); return v && v[0] == '1'; }();
+    for (uint32_t a = 0; a < 2; ++a) {
+        std::vector<uint32_t> &b = P.bnd[a];
+        b.clear();
+        if (order[a].empty()) continue;
+        const uint32_t nchunk = (maxend[a] + R - 1) / R;
+        if (!align_chunks) {
+            for (uint32_t c = 0; c <= nchunk; ++c) b.push_back((uint32_t)std::min<uint64_t>((uint64_t)c * R, 0xffffffffull));
+        } else {
+            std::vector<uint32_t> begins;
+            for (uint32_t i : order[a]) begins.push_back(sl[i].begin);
+            std::sort(begins.begin(), begins.end());
+            uint64_t cur = 0;
+            b.push_back(0);
+            while (cur < maxend[a]) {
+                const uint64_t target = cur + R;
+                // among the rows in (cur + R/2, target] the one at which the most slices begin, if at least 8 do
+                auto lo_it = std::upper_bound(begins.begin(), begins.end(), (uint32_t)std::min<uint64_t>(cur + R / 2, 0xffffffffull));
+                auto hi_it = std::upper_bound(begins.begin(), begins.end(), (uint32_t)std::min<uint64_t>(target, 0xffffffffull));
+                uint64_t next = target;
+                size_t best = 7;
+                for (auto it = lo_it; it != hi_it;) {
+                    auto run_end = std::upper_bound(it, hi_it, *it);
+                    if ((size_t)(run_end - it) > best) { best = (size_t)(run_end - it); next = *it; }
+                    it = run_end;
+                }
+                cur = next;
+                b.push_back((uint32_t)std::min<uint64_t>(cur, 0xffffffffull));
+            }
+        }
+    }
+    P.uniform_chunks = !align_chunks;
+    if (align_chunks)
+        for (uint32_t a = 0; a < 2; ++a) {
+            const std::vector<uint32_t> &b = P.bnd[a];
+            std::vector<uint32_t> &lut = P.bnd_lut[a];
+            lut.clear();
+            if (b.empty()) continue;
+            uint32_t c = 0;
+            for (uint64_t row = 0; row <= (uint64_t)b.back(); row += 4096) {
+                while (c + 1 < b.size() - 1 && row >= b[c + 1]) ++c;
+                lut.push_back(c);
+            }
+        }
+    for (uint32_t a = 0; a < 2; ++a)
+        for (uint32_t i : order[a]) incid += P.chunk_of(a, sl[i].end - 1) - P.chunk_of(a, sl[i].begin) + 1;
     P.incid = incid;
     if (incid < 65536) P.nthreads = 1;
     lap("collect");
@@ -245,7 +293,7 @@ void plan_begin(const QSlice *sl, uint32_t m, const PlanParams &pp, Plan &P)
     // tasks = (arena, block of chunks); the (C,T) arena first: its slices are short, so the GPU gets work early
     for (int a = 1; a >= 0; --a) {
         if (order[a].empty()) continue;
-        const uint32_t nchunk = (maxend[a] + R - 1) / R;
+        const uint32_t nchunk = (uint32_t)P.bnd[a].size() - 1;
         const uint32_t per = std::max(1u, (nchunk + 7) / 8);
         for (uint32_t c = 0; c < nchunk; c += per) P.tasks.push_back({(uint32_t)a, c, std::min(nchunk, c + per), 0});
     }
@@ -259,7 +307,7 @@ void plan_begin(const QSlice *sl, uint32_t m, const PlanParams &pp, Plan &P)
             }
         for (uint32_t a = 0; a < 2; ++a)
             for (uint32_t i : order[a]) {
-                const uint32_t lo = sl[i].begin / R, hi = (sl[i].end - 1) / R + 1;
+                const uint32_t lo = P.chunk_of(a, sl[i].begin), hi = P.chunk_of(a, sl[i].end - 1) + 1;
                 for (uint32_t t = lo / tper[a]; t <= (hi - 1) / tper[a]; ++t) {
                     Plan::Task &tk = P.tasks[tbase[a] + t];
                     const uint32_t l2 = std::max(lo, tk.c0), h2 = std::min(hi, tk.c1);
@@ -309,8 +357,8 @@ void plan_group(const QSlice *sl, Plan &P, size_t g, uint32_t &item_begin, uint3
         std::vector<uint32_t> &cstart = L.cstart, &fill = L.fill, &cur = L.cur;
         cstart.assign(nc + 1, 0);
         auto range = [&](uint32_t i, uint32_t &lo, uint32_t &hi) {     // chunks of query i inside this task, [lo, hi)
-            lo = std::max(sl[i].begin / R, tk.c0);
-            hi = std::min((sl[i].end - 1) / R + 1, tk.c1);
+            lo = std::max(P.chunk_of(tk.arena, sl[i].begin), tk.c0);
+            hi = std::min(P.chunk_of(tk.arena, sl[i].end - 1) + 1, tk.c1);
         };
         for (uint32_t i : ord) {
             uint32_t lo, hi;
@@ -326,8 +374,8 @@ void plan_group(const QSlice *sl, Plan &P, size_t g, uint32_t &item_begin, uint3
             for (uint32_t c = lo; c < hi; ++c) fill[cur[c - tk.c0]++] = i;
         }
         for (uint32_t c = 0; c < nc; ++c) {
-            const uint32_t c0 = (tk.c0 + c) * R;
-            const uint64_t c1 = (uint64_t)c0 + R;
+            const uint32_t c0 = P.bnd[tk.arena][tk.c0 + c];
+            const uint64_t c1 = P.bnd[tk.arena][tk.c0 + c + 1];
             for (uint32_t t = cstart[c]; t < cstart[c + 1]; t += BQ) {
                 const uint32_t te = std::min(cstart[c + 1], t + BQ);
                 TileItem it{};
