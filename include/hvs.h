@@ -52,11 +52,17 @@ typedef enum hvs_status {
 
 /* Which kernels solve() may use for the distance + top-100 step. */
 typedef enum hvs_mode {
-    HVS_MODE_AUTO = 0,    /* planner picks per bucket: tensor for large slices, FFMA tiles for medium, direct scan for small */
+    HVS_MODE_AUTO = 0,    /* slices that queries share: tcgen05 FP16 candidate sweep (K3) + exact FP32 re-rank (K5); sparse or tiny
+                             slices and tiny jobs: direct scan (K4).  One tile-kernel family per solve.  Results are exact. */
     HVS_MODE_EXACT = 1,   /* FP32 only: FFMA tile kernel (K2) + direct scan (K4); never touches tensor cores */
-    HVS_MODE_DIRECT = 2,  /* direct streaming scan only (K4): one CTA per query, reference arithmetic order */
-    HVS_MODE_TENSOR = 3   /* force the tcgen05 BF16 candidate pass (K3) + FP32 re-rank wherever a tile sweep is planned */
+    HVS_MODE_DIRECT = 2,  /* direct streaming scan only (K4): reference arithmetic order, no approximation anywhere */
+    HVS_MODE_TENSOR = 3   /* as AUTO, but the tcgen05 FP16 sweep (K3) is used wherever a tile sweep is possible, however small the job */
 } hvs_mode;
+
+#define HVS_FLAG_USE_GIVEN_STREAM 1u   /* hvs_config.stream is used as given, even if it is NULL (= legacy default stream) */
+#define HVS_FLAG_MARGIN_AUDIT 2u       /* K5 records, over every re-ranked survivor, the largest |approximate score - reference
+                                          distance| relative to the bound the candidate margins assume (hvs_stats.margin_audit;
+                                          must stay below 1).  Costs one atomic per survivor; results are unchanged. */
 
 typedef struct hvs_engine hvs_engine;
 
@@ -64,8 +70,13 @@ typedef struct hvs_config {
     uint32_t struct_size;   /* sizeof(hvs_config); lets the struct grow */
     int32_t device;         /* CUDA device ordinal; -1 = current device */
     uint32_t mode;          /* hvs_mode */
-    uint32_t flags;         /* reserved, 0 */
-    void *stream;           /* cudaStream_t to enqueue on; NULL = engine-owned stream */
+    uint32_t flags;         /* HVS_FLAG_* */
+    void *stream;           /* cudaStream_t to enqueue on.  NULL = the engine creates its own NON-BLOCKING stream (it does not
+                               synchronise with the legacy default stream), unless HVS_FLAG_USE_GIVEN_STREAM is set, in which
+                               case NULL means the legacy default stream itself.  The *_device entry points read and write
+                               their device buffers in stream order on THIS stream: work the caller queued on another stream
+                               (including an NCCL collective that produced an input) must be complete, or ordered before the
+                               call with an event the engine's stream waits on, before the call is made. */
     uint32_t id_offset;     /* added to every returned row id (data-sharded variant: first global row of this shard) */
     uint32_t reserved;
 } hvs_config;
@@ -98,6 +109,8 @@ typedef struct hvs_stats {
     float ms_solve_wall;        /* whole call, host wall clock */
     uint64_t pairs_tile;        /* share of `pairs` that belongs to queries solved by tile sweeps */
     uint64_t pairs_direct;      /* share of `pairs` that belongs to queries solved by the direct scan */
+    uint32_t n_outliers;        /* rows the index set aside as norm outliers (excluded from the approximate sweeps, scored exactly in K5) */
+    float margin_audit;         /* HVS_FLAG_MARGIN_AUDIT: max over re-ranked survivors of |s~ + ||q||^2 - d_ref| / eps  (0 when off) */
 } hvs_stats;
 
 HVS_API uint32_t hvs_abi_version(void);
@@ -141,6 +154,25 @@ HVS_API int hvs_solve(hvs_engine *e, const float *queries_host, uint32_t m, uint
 HVS_API int hvs_solve_device(hvs_engine *e, const float *queries_dev, uint32_t m, uint32_t *out_ids_dev);
 
 /*
+ * Query-sharded solve over `world` engines, one per GPU, every one holding the whole index (SURVEY 8e primary
+ * variant; the reference's parallel variant partitions the work of one vec_query call across its thread pool,
+ * include/optimized_parallel.hpp:100-157, include/threading.hpp:116-118 -- there the rows of D per query, here the
+ * queries: D is 4 GB and fits every GPU).  Every rank passes the SAME m queries.  The engine resolves all m
+ * predicates, assigns each query to a rank -- balanced by the rows the queries sweep, keeping queries that share rows
+ * on one rank (hvs_shard_assign_host is the same pure function, exposed for tests) -- and solves the queries of
+ * `rank`.  No communication happens here: the caller combines the ranks' rows (Python: sharding.solve_sharded, one
+ * NCCL all-gather).
+ *   out_order_host  : m query indices, rank-major; rank r owns out_order[sum(counts[0..r)) ...][counts[r]]
+ *   out_counts_host : world entries
+ *   out_ids_dev     : counts[rank] x 100 uint32 -- row i = the answer of query out_order[offset(rank) + i]  (size it m x 100)
+ */
+HVS_API int hvs_solve_shard_device(hvs_engine *e, const float *queries_dev, uint32_t m, uint32_t rank, uint32_t world,
+                                   uint32_t *out_ids_dev, uint32_t *out_order_host, uint32_t *out_counts_host);
+/* The assignment alone, from slices (arena 0 = T-ordered, 1 = (C,T)-ordered; rows [begin,end)); CPU only. */
+HVS_API int hvs_shard_assign_host(const uint32_t *arena, const uint32_t *begin, const uint32_t *end, uint32_t m,
+                                  uint32_t world, uint32_t *out_order, uint32_t *out_counts);
+
+/*
  * Data-sharded variant (mirrors include/optimized_parallel.hpp:100-157 at GPU scale):
  * each shard indexes its own rows (config.id_offset = first global row) and returns, per query,
  * its local best <= 100 (distance, global id) pairs ascending WITHOUT applying the pad rule, plus
@@ -176,7 +208,8 @@ HVS_API int hvs_solve_full(hvs_engine *e, const float *queries_host, uint32_t m,
 HVS_API int hvs_get_stats(const hvs_engine *e, hvs_stats *out);
 
 /* Runs `iters` launches of an FFMA-only microkernel on the engine's device and returns the best
- * achieved FP32 TFLOP/s (the denominator of the FFMA roofline; MEASURED_PEAKS.json has none). */
+ * achieved FP32 TFLOP/s (the denominator of the FFMA roofline; MEASURED_PEAKS.json has none).
+ * *out_sm_mhz (may be NULL) receives the SM clock that rate implies (TFLOP/s / (SMs x 128 lanes x 2)). */
 HVS_API int hvs_measure_ffma_peak(hvs_engine *e, uint32_t iters, float *out_tflops, float *out_sm_mhz);
 
 /*

@@ -30,13 +30,15 @@ LIB_PATH = os.path.join(HERE, "libhvs_b200.so")
 K, DIM, DROW, QROW = 100, 100, 102, 104
 
 MODE_AUTO, MODE_EXACT, MODE_DIRECT, MODE_TENSOR = 0, 1, 2, 3
+FLAG_USE_GIVEN_STREAM, FLAG_MARGIN_AUDIT = 1, 2
 HVS_OK, HVS_ERR_INVALID, HVS_ERR_NO_DEVICE, HVS_ERR_CUDA, HVS_ERR_STATE, HVS_ERR_NOMEM = 0, -1, -2, -3, -4, -5
 
 # every symbol include/hvs.h declares (tests check the library exports exactly these)
 ABI_SYMBOLS = (
     "hvs_abi_version", "hvs_last_error", "hvs_create", "hvs_destroy", "hvs_index_build", "hvs_index_build_device",
     "hvs_index_build_rows", "hvs_index_build_from_file",
-    "hvs_solve", "hvs_solve_full", "hvs_solve_device", "hvs_solve_partial_device", "hvs_merge_partials_device", "hvs_rescore",
+    "hvs_solve", "hvs_solve_full", "hvs_solve_device", "hvs_solve_shard_device", "hvs_shard_assign_host",
+    "hvs_solve_partial_device", "hvs_merge_partials_device", "hvs_rescore",
     "hvs_get_stats", "hvs_measure_ffma_peak", "hvs_plan_dryrun",
 )
 
@@ -60,7 +62,8 @@ class Stats(C.Structure):
                 ("ms_index_build", C.c_float), ("ms_h2d", C.c_float), ("ms_plan", C.c_float), ("ms_direct", C.c_float),
                 ("ms_tile", C.c_float), ("ms_tile_ffma", C.c_float), ("ms_tile_tensor", C.c_float),
                 ("ms_finalize", C.c_float), ("ms_d2h", C.c_float), ("ms_solve_device", C.c_float),
-                ("ms_solve_wall", C.c_float), ("pairs_tile", C.c_uint64), ("pairs_direct", C.c_uint64)]
+                ("ms_solve_wall", C.c_float), ("pairs_tile", C.c_uint64), ("pairs_direct", C.c_uint64),
+                ("n_outliers", C.c_uint32), ("margin_audit", C.c_float)]
 
     def as_dict(self) -> dict:
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "struct_size"}
@@ -104,6 +107,10 @@ def lib():
             f = getattr(L, name)
             f.restype = i32
             f.argtypes = [vp, vp, u32, vp]
+        L.hvs_solve_shard_device.restype = i32
+        L.hvs_solve_shard_device.argtypes = [vp, vp, u32, u32, u32, vp, vp, vp]
+        L.hvs_shard_assign_host.restype = i32
+        L.hvs_shard_assign_host.argtypes = [vp, vp, vp, u32, u32, vp, vp]
         L.hvs_solve_partial_device.restype = i32
         L.hvs_solve_partial_device.argtypes = [vp, vp, u32, vp, vp, vp]
         L.hvs_merge_partials_device.restype = i32
@@ -141,9 +148,9 @@ def _dev_ptr(t, dtype_name: str, numel: int) -> int:
 class Engine:
     """One engine = one GPU: hvs_create / hvs_index_build / hvs_solve / hvs_destroy."""
 
-    def __init__(self, device: int = -1, mode: int = MODE_AUTO, id_offset: int = 0, stream: int | None = None):
+    def __init__(self, device: int = -1, mode: int = MODE_AUTO, id_offset: int = 0, stream: int | None = None, flags: int = 0):
         self._h = C.c_void_p()
-        cfg = Config(struct_size=C.sizeof(Config), device=device, mode=mode, flags=0, stream=stream, id_offset=id_offset)
+        cfg = Config(struct_size=C.sizeof(Config), device=device, mode=mode, flags=flags, stream=stream, id_offset=id_offset)
         rc = lib().hvs_create(C.byref(self._h), C.byref(cfg))
         if rc != HVS_OK:
             raise HvsError(rc, lib().hvs_last_error(None).decode())
@@ -208,6 +215,17 @@ class Engine:
         m = queries_dev.shape[0]
         self._ck(lib().hvs_solve_device(self._h, _dev_ptr(queries_dev, "float32", m * QROW), m,
                                         _dev_ptr(out_dev, "int32", m * K)))
+
+    def solve_shard_device(self, queries_dev, rank: int, world: int, out_dev) -> tuple[np.ndarray, np.ndarray]:
+        """Query-sharded solve (hvs_solve_shard_device): this rank's share of the batch every rank passes.
+        -> (order[m] rank-major query indices, counts[world]); out_dev[:counts[rank]] holds the answers of
+        order[offset(rank):][:counts[rank]].  No communication: sharding.solve_sharded combines the ranks."""
+        m = queries_dev.shape[0]
+        order = np.empty(m, np.uint32)
+        counts = np.zeros(world, np.uint32)
+        self._ck(lib().hvs_solve_shard_device(self._h, _dev_ptr(queries_dev, "float32", m * QROW), m, rank, world,
+                                              _dev_ptr(out_dev, "int32", m * K), order.ctypes.data, counts.ctypes.data))
+        return order, counts
 
     def solve_partial_device(self, queries_dev, out_dist_dev, out_ids_dev, out_count_dev) -> None:
         m = queries_dev.shape[0]
@@ -310,6 +328,21 @@ def compare_dist(a: np.ndarray, b: np.ndarray, error_delta: float = 0.002) -> di
 
 def compare_dist_files(a_path: str, b_path: str, error_delta: float = 0.002) -> dict:
     return compare_dist(read_knn_dist(a_path), read_knn_dist(b_path), error_delta)
+
+
+def shard_assign(arena, begin, end, world: int):
+    """hvs_shard_assign_host (CPU only): -> (order[m] rank-major query indices, counts[world])."""
+    arena = np.ascontiguousarray(arena, np.uint32)
+    begin = np.ascontiguousarray(begin, np.uint32)
+    end = np.ascontiguousarray(end, np.uint32)
+    m = arena.shape[0]
+    order = np.empty(m, np.uint32)
+    counts = np.zeros(world, np.uint32)
+    rc = lib().hvs_shard_assign_host(arena.ctypes.data, begin.ctypes.data, end.ctypes.data, m, world, order.ctypes.data,
+                                     counts.ctypes.data)
+    if rc != HVS_OK:
+        raise HvsError(rc, "hvs_shard_assign_host: invalid slices or world")
+    return order, counts
 
 
 def plan_dryrun(arena, begin, end, mode: int = MODE_EXACT, max_items: int = 1 << 20):

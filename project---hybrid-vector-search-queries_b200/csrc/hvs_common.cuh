@@ -29,7 +29,9 @@ struct Arena {
     const float *x;          // [n][100] fp32, 400-byte rows
     const uint32_t *ids;     // [n] original row id (+ id_offset)
     const float *xnorm;      // [n] ||x||^2
-    const void *xb;          // bf16 image for the tensor path (may be null)
+    const void *xb;          // fp16 image for the tensor path (may be null)
+    const uint32_t *outl;    // ascending arena positions of the norm-outlier rows (xnorm = +inf there): K5 scores them exactly
+    uint32_t n_outl;
 };
 
 // ---- order-preserving float keys ------------------------------------------------------------

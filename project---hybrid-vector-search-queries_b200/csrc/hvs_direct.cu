@@ -26,7 +26,7 @@ struct DirectSmem {
 
 __global__ void __launch_bounds__(DT, 2)
 k_direct(const float *__restrict__ queries, const QSlice *__restrict__ slices, const uint32_t *__restrict__ q_list,
-         Arena a0, Arena a1, const float *__restrict__ tail, uint32_t n_total, int partial,
+         Arena a0, Arena a1, const float *__restrict__ tail, uint32_t n_total, uint32_t id_offset, int partial,
          uint32_t *__restrict__ out_ids, float *__restrict__ out_dist, uint32_t *__restrict__ out_count)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -61,33 +61,32 @@ k_direct(const float *__restrict__ queries, const QSlice *__restrict__ slices, c
     for (uint32_t it = 0; it < ntiles; ++it) {
         mbar_wait(&S.bar[it & 1], (it >> 1) & 1);
         const uint32_t rows = min((uint32_t)DT, len - it * DT);
+        bool high = false;                     // one of my pushes took a slot past the compaction mark
         if ((uint32_t)tid < rows) {
             float d = ref_dist_row(S.x[it & 1] + tid * DIM, S.q);
-            if (d < S.top.thr) S.top.push(d, sl.begin + it * DT + tid);
+            if (d < S.top.thr) high = S.top.push(d, sl.begin + it * DT + tid) >= (uint32_t)(DCAP - DT);
         }
-        __syncthreads();                       // tile consumed, pushes visible
+        const bool need = __syncthreads_or(high);   // tile consumed, pushes visible; the decision is block-uniform
         if (tid == 0 && it + 2 < ntiles) issue(it + 2);
-        if (S.top.cnt > (uint32_t)(DCAP - DT)) S.top.compact(tid, DT, 0.f, K);
+        if (need) S.top.compact(tid, DT, 0.f, K);
     }
     __syncthreads();
-    finish_query(S.top, S.q, A, len, tail, n_total, q, partial != 0, out_ids, out_dist, out_count, tid, DT);
+    finish_query(S.top, S.q, A, len, tail, n_total, id_offset, q, partial != 0, out_ids, out_dist, out_count, tid, DT);
+}
+
+cudaError_t direct_init_attributes()     // per device; called by hvs_create with the engine's device current
+{
+    return cudaFuncSetAttribute(k_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DirectSmem));
 }
 
 cudaError_t launch_direct(hvs_engine *e, const float *queries_dev, const QSlice *slices_dev, const uint32_t *q_list_dev,
                           uint32_t nq, bool partial, uint32_t *out_ids, float *out_dist, uint32_t *out_count)
 {
     if (!nq) return cudaSuccess;
-    static bool attr_done_dev[64] = {false};                  // the attribute is per device
-    bool &attr_done = attr_done_dev[e->device & 63];
     const int smem = (int)sizeof(DirectSmem);
-    if (!attr_done) {
-        cudaError_t c = cudaFuncSetAttribute(k_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (c != cudaSuccess) return c;
-        attr_done = true;
-    }
     const Index &ix = e->index;
     k_direct<<<nq, DT, smem, e->stream>>>(queries_dev, slices_dev, q_list_dev, ix.arena(0), ix.arena(1),
-                                           ix.tail.as<float>(), ix.n_total, partial ? 1 : 0, out_ids, out_dist, out_count);
+                                           ix.tail.as<float>(), ix.n_total, ix.id_offset, partial ? 1 : 0, out_ids, out_dist, out_count);
     return cudaGetLastError();
 }
 

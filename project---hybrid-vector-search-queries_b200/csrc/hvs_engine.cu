@@ -77,22 +77,29 @@ extern "C" int hvs_create(hvs_engine **out, const hvs_config *cfg)
     e->device = dev;
     e->mode = c.mode;
     e->id_offset = c.id_offset;
+    e->flags = c.flags;
+    if (const char *v = getenv("HVS_MARGIN_AUDIT")) if (v[0] == '1') e->flags |= HVS_FLAG_MARGIN_AUDIT;
     e->sm_count = prop.multiProcessorCount;
-    if (c.stream) { e->stream = (cudaStream_t)c.stream; e->own_stream = false; }
+    cudaError_t cc = cudaSuccess;
+    auto keep = [&](cudaError_t r) { if (cc == cudaSuccess) cc = r; };
+    if (c.stream || (c.flags & HVS_FLAG_USE_GIVEN_STREAM)) { e->stream = (cudaStream_t)c.stream; e->own_stream = false; }
     else {
-        if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) {
-            g_create_err = "hvs_create: cudaStreamCreate failed";
-            delete e;
-            return HVS_ERR_CUDA;
-        }
-        e->own_stream = true;
+        keep(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+        e->own_stream = cc == cudaSuccess;
     }
-    for (auto &ev : e->ev) cudaEventCreate(&ev);
-    for (auto &ev : e->evg) cudaEventCreate(&ev);
-    for (auto &ev : e->ev_sync) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-    cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking);
-    cudaStreamCreateWithFlags(&e->stream_up, cudaStreamNonBlocking);
-    for (auto &ev : e->ev_up) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    for (auto &ev : e->ev) keep(cudaEventCreate(&ev));
+    for (auto &ev : e->evg) keep(cudaEventCreate(&ev));
+    for (auto &ev : e->ev_sync) keep(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    keep(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
+    keep(cudaStreamCreateWithFlags(&e->stream_up, cudaStreamNonBlocking));
+    for (auto &ev : e->ev_up) keep(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    if (cc == cudaSuccess) cc = init_kernel_attributes();      // dynamic shared-memory opt-in of every kernel, for this device
+    if (cc != cudaSuccess) {
+        g_create_err = std::string("hvs_create: ") + cudaGetErrorString(cc);
+        cudaGetLastError();
+        hvs_destroy(e);
+        return HVS_ERR_CUDA;
+    }
     e->stats.struct_size = sizeof(hvs_stats);
     *out = e;
     return HVS_OK;
@@ -102,22 +109,22 @@ extern "C" void hvs_destroy(hvs_engine *e)
 {
     if (!e) return;
     cudaSetDevice(e->device);
-    cudaStreamSynchronize(e->stream);
+    if (e->own_stream ? e->stream != nullptr : true) cudaStreamSynchronize(e->stream);
     Index &ix = e->index;
     for (int a = 0; a < 2; ++a) { ix.x[a].release(); ix.ids[a].release(); ix.xnorm[a].release(); ix.xb[a].release(); }
-    ix.keys_t.release(); ix.keys_ct.release(); ix.tail.release(); ix.inv_t.release();
+    ix.keys_t.release(); ix.keys_ct.release(); ix.tail.release(); ix.inv_t.release(); ix.outl[0].release(); ix.outl[1].release();
     DevBuf *bufs[] = {&e->d_queries, &e->d_out, &e->d_slices, &e->d_direct_q, &e->d_items, &e->d_item_q, &e->d_tile_q,
                       &e->d_qoff, &e->d_qlists, &e->d_cand, &e->d_cand_cnt, &e->d_scratch, &e->d_flags, &e->d_gthr, &e->d_pool, &e->d_gbest, &e->d_glock,
-                      &e->d_work_counter, &e->d_rescore_ids, &e->d_rescore_out};
+                      &e->d_work_counter, &e->d_rescore_ids, &e->d_rescore_out, &e->d_audit, &e->d_shard_q, &e->d_shard_sl, &e->d_shard_own};
     for (DevBuf *b : bufs) b->release();
-    e->h_slices.release(); e->h_stage.release(); e->h_ingest[0].release(); e->h_ingest[1].release();
+    e->h_slices.release(); e->h_flags.release(); e->h_stage_own.release(); e->h_stage.release(); e->h_ingest[0].release(); e->h_ingest[1].release();
     for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : e->evg) if (ev) cudaEventDestroy(ev);
     for (auto &ev : e->ev_sync) if (ev) cudaEventDestroy(ev);
     if (e->stream2) cudaStreamDestroy(e->stream2);
     if (e->stream_up) cudaStreamDestroy(e->stream_up);
     for (auto &ev : e->ev_up) if (ev) cudaEventDestroy(ev);
-    if (e->own_stream) cudaStreamDestroy(e->stream);
+    if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
 
@@ -145,37 +152,60 @@ extern "C" int hvs_index_build_device(hvs_engine *e, const float *rows_dev, uint
     e->stats.ms_index_build = ev_ms(e->ev[0], e->ev[1]);
     e->stats.n = e->index.n;
     e->stats.n_total = e->index.n_total;
+    e->stats.n_outliers = e->index.n_outl[0];
     return HVS_OK;
 }
 
 // ---- solve ----------------------------------------------------------------------------------
-static int solve_impl(hvs_engine *e, const float *q_dev, uint32_t m, bool partial, uint32_t *out_ids, float *out_dist,
-                      uint32_t *out_count)
+// Everything after the slices are known on both sides (d_sl on the device, h_sl on the host): plan, sweeps, finalize.
+// e->ev[2] must have been recorded on the stream before the slice search.
+static int solve_core(hvs_engine *e, const float *q_dev, uint32_t m, const QSlice *d_sl, const QSlice *h_sl, bool partial,
+                      uint32_t *out_ids, float *out_dist, uint32_t *out_count);
+
+static void reset_solve_stats(hvs_engine *e, uint32_t m)
 {
     hvs_stats &st = e->stats;
     st.m = m;
     st.pairs = st.pairs_computed = st.rows_union = st.pairs_tile = st.pairs_direct = 0;
     st.n_direct = st.n_tile = st.n_items_ffma = st.n_items_tensor = st.n_fallback = st.launches = 0;
     st.ms_plan = st.ms_direct = st.ms_tile = st.ms_tile_ffma = st.ms_tile_tensor = st.ms_finalize = st.ms_solve_device = 0.f;
+    st.margin_audit = 0.f;
+}
+
+static int solve_impl(hvs_engine *e, const float *q_dev, uint32_t m, bool partial, uint32_t *out_ids, float *out_dist,
+                      uint32_t *out_count)
+{
+    reset_solve_stats(e, m);
     if (!m) return HVS_OK;
     cudaStream_t s = e->stream;
     ECUDA(e->d_slices.ensure((size_t)m * sizeof(QSlice)));
     ECUDA(e->h_slices.ensure((size_t)m * sizeof(QSlice)));
     QSlice *d_sl = e->d_slices.as<QSlice>();
-
     cudaEventRecord(e->ev[2], s);
     ECUDA(launch_plan_search(e, q_dev, m, d_sl));
-    st.launches++;
+    e->stats.launches++;
     ECUDA(cudaMemcpyAsync(e->h_slices.p, d_sl, (size_t)m * sizeof(QSlice), cudaMemcpyDeviceToHost, s));
     ECUDA(cudaStreamSynchronize(s));
+    return solve_core(e, q_dev, m, d_sl, e->h_slices.as<QSlice>(), partial, out_ids, out_dist, out_count);
+}
+
+static int solve_core(hvs_engine *e, const float *q_dev, uint32_t m, const QSlice *d_sl, const QSlice *h_sl, bool partial,
+                      uint32_t *out_ids, float *out_dist, uint32_t *out_count)
+{
+    hvs_stats &st = e->stats;
+    cudaStream_t s = e->stream;
+    if (e->flags & HVS_FLAG_MARGIN_AUDIT) {
+        ECUDA(e->d_audit.ensure(4));
+        ECUDA(cudaMemsetAsync(e->d_audit.p, 0, 4, s));
+    }
 
     PlanParams pp;
     pp.mode = e->mode;
-    pp.tensor_available = tensor_path_available() && e->index.xb[0].p != nullptr;
+    pp.tensor_available = e->index.xb[0].p != nullptr && e->index.xb[1].p != nullptr;
+    pp.approx_ok = e->index.approx_ok;
     static const long long min_pairs_env = [] { const char *v = getenv("HVS_MIN_TILE_PAIRS"); return v ? atoll(v) : -1ll; }();
     if (min_pairs_env >= 0) pp.min_tile_pairs = (uint64_t)min_pairs_env;   // tests set 0: tile kernels run on tiny inputs too
     Plan &P = e->plan;
-    const QSlice *h_sl = e->h_slices.as<QSlice>();
     plan_begin(h_sl, m, pp, P);                      // classify; tile queries are cut into groups of chunk blocks
     st.pairs = P.pairs;
     st.pairs_tile = P.pairs_tile;
@@ -279,9 +309,10 @@ static int solve_impl(hvs_engine *e, const float *q_dev, uint32_t m, bool partia
         st.launches++;
         cudaEventRecord(e->ev[8], s);
         // queries whose candidate buffers overflowed their margin guarantee are re-solved exactly by K4
-        ECUDA(cudaMemcpyAsync(e->h_slices.p, e->d_flags.p, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
+        ECUDA(e->h_flags.ensure((size_t)m * 4));
+        ECUDA(cudaMemcpyAsync(e->h_flags.p, e->d_flags.p, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
         ECUDA(cudaStreamSynchronize(s));
-        const uint32_t *fl = e->h_slices.as<uint32_t>();
+        const uint32_t *fl = e->h_flags.as<uint32_t>();
         std::vector<uint32_t> redo;
         for (uint32_t q : P.tile_q) if (fl[q]) redo.push_back(q);
         if (!redo.empty()) {
@@ -294,6 +325,7 @@ static int solve_impl(hvs_engine *e, const float *q_dev, uint32_t m, bool partia
         }
     }
     cudaEventRecord(e->ev[9], s);
+    if (e->flags & HVS_FLAG_MARGIN_AUDIT) ECUDA(cudaMemcpyAsync(&st.margin_audit, e->d_audit.p, 4, cudaMemcpyDeviceToHost, s));
     ECUDA(cudaStreamSynchronize(s));
     ECUDA(cudaGetLastError());
     st.ms_plan = ev_ms(e->ev[2], e->ev[3]);          // slice search + classification; group planning overlaps the sweeps
@@ -366,6 +398,54 @@ extern "C" int hvs_solve(hvs_engine *e, const float *queries_host, uint32_t m, u
     e->stats.ms_d2h = ev_ms(e->ev[10], e->ev[11]);
     e->stats.ms_solve_wall = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return HVS_OK;
+}
+
+// Query-sharded solve: this rank's share of one batch (see shard_assign, hvs_plan.cu).
+extern "C" int hvs_solve_shard_device(hvs_engine *e, const float *queries_dev, uint32_t m, uint32_t rank, uint32_t world,
+                                      uint32_t *out_ids_dev, uint32_t *out_order_host, uint32_t *out_counts_host)
+{
+    int rc = check_solve_args(e, queries_dev, m, out_ids_dev);
+    if (rc) return rc;
+    if (!world || world > 255 || rank >= world) EFAIL(HVS_ERR_INVALID, "hvs_solve_shard_device: need rank < world <= 255");
+    if (!out_counts_host || (m && !out_order_host)) EFAIL(HVS_ERR_INVALID, "hvs_solve_shard_device: NULL buffer");
+    auto t0 = std::chrono::steady_clock::now();
+    e->stats.ms_h2d = e->stats.ms_d2h = 0.f;
+    reset_solve_stats(e, 0);
+    for (uint32_t r = 0; r < world; ++r) out_counts_host[r] = 0;
+    if (!m) return HVS_OK;
+    cudaStream_t s = e->stream;
+    ECUDA(e->d_slices.ensure((size_t)m * sizeof(QSlice)));
+    ECUDA(e->h_slices.ensure((size_t)m * sizeof(QSlice)));
+    QSlice *d_sl_all = e->d_slices.as<QSlice>();
+    cudaEventRecord(e->ev[2], s);
+    ECUDA(launch_plan_search(e, queries_dev, m, d_sl_all));                 // every rank resolves ALL predicates (two binary searches each)
+    ECUDA(cudaMemcpyAsync(e->h_slices.p, d_sl_all, (size_t)m * sizeof(QSlice), cudaMemcpyDeviceToHost, s));
+    ECUDA(cudaStreamSynchronize(s));
+    const QSlice *h_all = e->h_slices.as<QSlice>();
+    shard_assign(h_all, m, world, out_order_host, out_counts_host);        // the same on every rank
+    uint32_t off = 0;
+    for (uint32_t r = 0; r < rank; ++r) off += out_counts_host[r];
+    const uint32_t m_own = out_counts_host[rank];
+    const uint32_t *own = out_order_host + off;
+    reset_solve_stats(e, m_own);
+    e->stats.launches = 1;
+    if (m_own) {
+        e->h_shard_sl.resize(m_own);
+        for (uint32_t i = 0; i < m_own; ++i) e->h_shard_sl[i] = h_all[own[i]];
+        ECUDA(e->d_shard_own.ensure((size_t)m_own * 4));
+        ECUDA(e->d_shard_q.ensure((size_t)m_own * QROW * 4));
+        ECUDA(e->d_shard_sl.ensure((size_t)m_own * sizeof(QSlice)));
+        ECUDA(e->h_stage_own.ensure((size_t)m_own * 4));
+        std::memcpy(e->h_stage_own.p, own, (size_t)m_own * 4);
+        ECUDA(cudaMemcpyAsync(e->d_shard_own.p, e->h_stage_own.p, (size_t)m_own * 4, cudaMemcpyHostToDevice, s));
+        ECUDA(launch_gather_queries(e, queries_dev, d_sl_all, e->d_shard_own.as<uint32_t>(), m_own, e->d_shard_q.as<float>(),
+                                    e->d_shard_sl.as<QSlice>()));
+        e->stats.launches++;
+        rc = solve_core(e, e->d_shard_q.as<float>(), m_own, e->d_shard_sl.as<QSlice>(), e->h_shard_sl.data(), false, out_ids_dev,
+                        nullptr, nullptr);
+    }
+    e->stats.ms_solve_wall = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return rc;
 }
 
 extern "C" int hvs_solve_full(hvs_engine *e, const float *queries_host, uint32_t m, uint32_t *out_ids_host, float *out_dist_host)

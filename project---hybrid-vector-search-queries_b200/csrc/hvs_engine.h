@@ -15,6 +15,10 @@ namespace hvs {
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
     cudaError_t ensure(size_t bytes)
     {
         if (bytes <= cap) return cudaSuccess;
@@ -32,6 +36,10 @@ struct DevBuf {
 struct HostPinned {
     void *p = nullptr;
     size_t cap = 0;
+    HostPinned() = default;
+    HostPinned(const HostPinned &) = delete;
+    HostPinned &operator=(const HostPinned &) = delete;
+    ~HostPinned() { release(); }
     cudaError_t ensure(size_t bytes)
     {
         if (bytes <= cap) return cudaSuccess;
@@ -59,7 +67,10 @@ struct Index {
     DevBuf keys_ct;            // [n] u64  sorted ord(C)<<32 | ord(T)
     DevBuf tail;               // [100][100] fp32: tail[s-1] = vector of row n_total - s  (pad rule)
     DevBuf inv_t;              // [n_total] u32: original row -> arena-T row (0xFFFFFFFF if not indexed); rescore only
-    float xnorm_max = 0.f;     // max ||x||^2 over indexed rows (margin bound)
+    DevBuf outl[2];            // [n_outl] u32: arena positions (ascending) of the outlier rows -- excluded from K2/K3, scored exactly by K5
+    uint32_t n_outl[2] = {0, 0};
+    bool approx_ok = true;     // false: too many non-finite rows; no approximate sweep may run (everything takes K4)
+    float xnorm_max = 0.f;     // max ||x||^2 over indexed non-outlier rows (margin bound)
     float img_scale = 1.f;     // sx: power of two applied to x before the fp16 image is written (K3)
     bool built = false;
     Arena arena(int a) const
@@ -67,6 +78,7 @@ struct Index {
         Arena r;
         r.x = x[a].as<float>(); r.ids = ids[a].as<uint32_t>(); r.xnorm = xnorm[a].as<float>();
         r.xb = xb[a].p;
+        r.outl = outl[a].as<uint32_t>(); r.n_outl = n_outl[a];
         return r;
     }
 };
@@ -76,7 +88,8 @@ constexpr int QT = 128;          // queries per FFMA tile item (K2)
 constexpr int QT_TENSOR = 256;   // queries per tensor tile item (K3): two M=128 halves share every data stage
 constexpr int KOUT = 256;        // candidates an item hands to finalize per query (<= this many)
 constexpr int TENSOR_POOL = 512; // K3: survivor pool entries per (CTA, query) in global memory
-constexpr int TENSOR_GBEST = 128; // K3: per-query global list of the best scores seen by any CTA
+constexpr int TENSOR_GBEST = 128;
+constexpr int OUTLIER_MAX = 256;  // K0: most rows that may be set aside as norm outliers // K3: per-query global list of the best scores seen by any CTA
 
 struct TileItem {              // one CTA-sized unit of work: <= 128 queries sweep arena rows [row_begin,row_end)
     uint32_t arena;
@@ -142,8 +155,12 @@ struct PlanParams {
     uint64_t min_tile_pairs = 4000000;    // below this many (query,row) pairs a tile sweep's fixed cost (~0.5 ms: persistent launch, operand
                                           // build, finalize) exceeds the direct scan of all of them: everything goes direct
     bool tensor_available = false;
+    bool approx_ok = true;                // false: the index allows no approximate sweep (Index::approx_ok)
 };
 
+constexpr uint64_t SHARD_QUERY_COST = 400000;   // shard_assign: fixed cost of a query, in (query,row) pairs (warm-up + finalize)
+constexpr uint32_t SHARD_STRIPES = 16;          // shard_assign: segments per rank
+void shard_assign(const QSlice *slices, uint32_t m, uint32_t world, uint32_t *order, uint32_t *counts);
 void plan_build(const QSlice *slices, uint32_t m, const PlanParams &pp, Plan &out);     // begin + every group + finish
 void plan_begin(const QSlice *slices, uint32_t m, const PlanParams &pp, Plan &out);     // classify, order, cut into groups
 void plan_group(const QSlice *slices, Plan &out, size_t g, uint32_t &item_begin, uint32_t &item_end);   // items of one group
@@ -155,6 +172,7 @@ struct hvs_engine {
     int device = 0;
     uint32_t mode = HVS_MODE_AUTO;
     uint32_t id_offset = 0;
+    uint32_t flags = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaStream_t stream2 = nullptr;   // second lane for tile launches: the tail of group g overlaps the head of group g + 1
@@ -169,8 +187,10 @@ struct hvs_engine {
     hvs_stats stats{};
     // per-solve scratch (grow-only)
     hvs::DevBuf d_queries, d_out, d_slices, d_direct_q, d_items, d_item_q, d_tile_q, d_qoff, d_qlists;
-    hvs::DevBuf d_cand, d_cand_cnt, d_scratch, d_flags, d_gthr, d_pool, d_gbest, d_glock, d_work_counter, d_rescore_ids, d_rescore_out;
-    hvs::HostPinned h_slices, h_stage, h_ingest[2];
+    hvs::DevBuf d_cand, d_cand_cnt, d_scratch, d_flags, d_gthr, d_pool, d_gbest, d_glock, d_work_counter, d_rescore_ids, d_rescore_out, d_audit, d_shard_q, d_shard_sl, d_shard_own;
+    std::vector<hvs::QSlice> h_shard_sl;
+    std::vector<uint32_t> h_shard_order, h_shard_counts;
+    hvs::HostPinned h_slices, h_flags, h_stage_own, h_stage, h_ingest[2];
     cudaEvent_t ev[12]{};
     cudaEvent_t evg[16]{};     // start/end of each group's tile launch
     hvs::Plan plan;
@@ -180,6 +200,9 @@ namespace hvs {
 // each returns cudaSuccess or the failing error (message left in e->err)
 cudaError_t index_build_device(hvs_engine *e, const float *rows_dev, uint32_t n_total, float sample_proportion);
 cudaError_t launch_plan_search(hvs_engine *e, const float *queries_dev, uint32_t m, QSlice *slices_dev);
+// q_sub[i] = queries[own[i]], sl_sub[i] = slices[own[i]]  (the queries a rank owns, made contiguous)
+cudaError_t launch_gather_queries(hvs_engine *e, const float *queries_dev, const QSlice *slices_dev, const uint32_t *own_dev,
+                                  uint32_t n_own, float *q_sub, QSlice *sl_sub);
 // K4: solve `nq` queries listed in q_list_dev (or all 0..nq-1 if null) by direct scan.
 // partial == false: writes out_ids[q][100] with the pad rule applied.
 // partial == true : writes out_dist/out_ids (ascending, unused = +inf/0xFFFFFFFF) and out_count, no pad.
@@ -206,5 +229,14 @@ cudaError_t launch_merge_partials(hvs_engine *e, const float *queries_dev, uint3
 cudaError_t launch_rescore(hvs_engine *e, const float *queries_dev, uint32_t m, const uint32_t *ids_dev, float *out_dev,
                            const float *rows_unused);
 cudaError_t measure_ffma_peak(hvs_engine *e, uint32_t iters, float *tflops, float *mhz);
-bool tensor_path_available();
+cudaError_t direct_init_attributes();
+cudaError_t tile_ffma_init_attributes();
+cudaError_t tile_tensor_init_attributes();
+inline cudaError_t init_kernel_attributes()
+{
+    cudaError_t c = direct_init_attributes();
+    if (c == cudaSuccess) c = tile_ffma_init_attributes();
+    if (c == cudaSuccess) c = tile_tensor_init_attributes();
+    return c;
+}
 }  // namespace hvs

@@ -19,7 +19,7 @@ constexpr int P1CAP = 2048;    // approximate-score selection buffer (>= P1KEEP 
 constexpr int P1KEEP = 512;    // most rows that may sit inside the margin before we give up
 struct FinSmem {
     TopBuf<P1CAP, true> p1;
-    TopBuf<P1KEEP + 128, false> p2;
+    TopBuf<1024, false> p2;        // a power of two >= P1KEEP + FT: compact() pads its bitonic sort up to the next power of two
     alignas(16) float q[DIM];
 };
 }  // namespace
@@ -28,7 +28,8 @@ __global__ void __launch_bounds__(FT)
 k_finalize(const float *__restrict__ queries, const QSlice *__restrict__ slices, const uint32_t *__restrict__ tile_q,
            const uint32_t *__restrict__ qoff, const uint32_t *__restrict__ qlists, const uint64_t *__restrict__ cand,
            const uint32_t *__restrict__ cand_cnt, uint32_t *__restrict__ flags, Arena a0, Arena a1,
-           const float *__restrict__ tail, uint32_t n_total, float xnorm_max, float tensor_sx, int partial,
+           const float *__restrict__ tail, uint32_t n_total, uint32_t id_offset, float xnorm_max, float tensor_sx, int partial,
+           uint32_t *__restrict__ audit,
            uint32_t *__restrict__ out_ids, float *__restrict__ out_dist, uint32_t *__restrict__ out_count)
 {
     __shared__ FinSmem S;
@@ -66,6 +67,7 @@ k_finalize(const float *__restrict__ queries, const QSlice *__restrict__ slices,
         for (uint32_t i0 = 0; i0 < nl;) {
             uint32_t i1 = i0, sum = 0;                            // every thread walks the same lengths: uniform
             while (i1 < nl && sum + s_len[i1] <= P1ROUND) sum += s_len[i1++];
+            bool high = false;                                    // one of my pushes took a slot past the compaction mark
             for (uint32_t i = i0 + warp; i < i1; i += FT / 32) {
                 const uint32_t list = s_list[i], c = s_len[i];
                 for (uint32_t e = lane; e < c; e += 32) {
@@ -74,11 +76,12 @@ k_finalize(const float *__restrict__ queries, const QSlice *__restrict__ slices,
                     if (sc < S.p1.thr) {
                         const uint32_t slot = atomicAdd(&S.p1.cnt, 1u);
                         S.p1.cand[slot] = k;                     // cnt <= P1CAP - P1ROUND before every batch
+                        high |= slot >= (uint32_t)(P1CAP - P1ROUND);
                     }
                 }
             }
-            __syncthreads();
-            if (S.p1.cnt > (uint32_t)(P1CAP - P1ROUND)) S.p1.compact_select<FT>(tid, margin, P1KEEP);
+            // block-uniform decision (a plain read of cnt after the barrier would race with the next batch's pushes)
+            if (__syncthreads_or(high)) S.p1.compact_select<FT>(tid, margin, P1KEEP);
             i0 = i1;
         }
         __syncthreads();                                          // s_list / s_len are rewritten by the next chunk
@@ -86,16 +89,43 @@ k_finalize(const float *__restrict__ queries, const QSlice *__restrict__ slices,
     S.p1.compact_select<FT>(tid, margin, P1KEEP);
     if (S.p1.overflow && tid == 0) flags[q] = 1u;            // K4 re-solves this query
 
-    // phase 2: the reference's arithmetic on the survivors
+    // phase 2: the reference's arithmetic on the survivors.  Norm outliers (K0: ||x||^2 = +inf) are dropped here --
+    // a K3 pool can pick them up while a query has no threshold yet -- because the pass below scores ALL of them.
     const int c1 = (int)S.p1.cnt;
+    const float INF = __int_as_float(0x7f800000);
     for (int i = tid; i < c1; i += FT) {
         const uint32_t row = (uint32_t)S.p1.cand[i];
+        if (A.n_outl && !(A.xnorm[row] < INF)) continue;
         const float d = ref_dist_row(A.x + (size_t)row * DIM, S.q);
-        S.p2.cand[i] = pack_key(d, row);
+        S.p2.push(d, row);                                        // <= P1KEEP entries
+        if (audit) {
+            // HVS_FLAG_MARGIN_AUDIT: the bound the margins rest on, measured.  s~ is in units of sx^2 d for K3 lists; the
+            // margin is 2 eps (hvs_margin.cuh), so |s~ / sx^2 + ||q||^2 - d_ref| / (margin / 2 / sx^2) must stay below 1.
+            const float unit = tensor_sx > 0.f ? tensor_sx * tensor_sx : 1.f;
+            const float st = okey_inv((uint32_t)(S.p1.cand[i] >> 32));
+            const float err = fabsf(st / unit + sl.qnorm - d);
+            const float ratio = err / (0.5f * margin / unit);
+            if (ratio == ratio) atomicMax(audit, __float_as_uint(ratio));     // non-negative floats order like their bits
+        }
     }
-    if (tid == 0) S.p2.cnt = c1;
     __syncthreads();
-    finish_query(S.p2, S.q, A, len, tail, n_total, q, partial != 0, out_ids, out_dist, out_count, tid, FT);
+    // the outlier rows inside this query's slice never went through the approximate sweep: score them all, exactly
+    if (A.n_outl) {
+        uint32_t lo = 0, hi = A.n_outl;
+        for (uint32_t l = 0, h = A.n_outl; l < h;) { const uint32_t mid = (l + h) >> 1; if (A.outl[mid] < sl.begin) l = mid + 1; else h = mid; lo = l; }
+        for (uint32_t l = lo, h = A.n_outl; l < h;) { const uint32_t mid = (l + h) >> 1; if (A.outl[mid] < sl.end) l = mid + 1; else h = mid; hi = l; }
+        if (lo > hi) hi = lo;
+        for (uint32_t b = lo; b < hi; b += FT) {                  // block-uniform trip count
+            bool high = false;
+            if (b + tid < hi) {
+                const uint32_t row = A.outl[b + tid];
+                const float d = ref_dist_row(A.x + (size_t)row * DIM, S.q);
+                if (d < S.p2.thr || !(d == d)) high = S.p2.push(d, row) >= (uint32_t)P1KEEP;
+            }
+            if (__syncthreads_or(high)) S.p2.compact(tid, FT, 0.f, K);    // exact distances: margin 0
+        }
+    }
+    finish_query(S.p2, S.q, A, len, tail, n_total, id_offset, q, partial != 0, out_ids, out_dist, out_count, tid, FT);
 }
 
 cudaError_t launch_finalize(hvs_engine *e, const float *queries_dev, const QSlice *slices_dev, const uint32_t *tile_q_dev,
@@ -106,8 +136,9 @@ cudaError_t launch_finalize(hvs_engine *e, const float *queries_dev, const QSlic
     if (!n_tile_q) return cudaSuccess;
     const Index &ix = e->index;
     k_finalize<<<n_tile_q, FT, 0, e->stream>>>(queries_dev, slices_dev, tile_q_dev, qoff_dev, qlists_dev, cand_dev, cand_cnt_dev,
-                                                flags_dev, ix.arena(0), ix.arena(1), ix.tail.as<float>(), ix.n_total,
-                                                ix.xnorm_max, e->plan.n_tensor ? ix.img_scale : 0.f, partial ? 1 : 0, out_ids,
+                                                flags_dev, ix.arena(0), ix.arena(1), ix.tail.as<float>(), ix.n_total, ix.id_offset,
+                                                ix.xnorm_max, e->plan.n_tensor ? ix.img_scale : 0.f, partial ? 1 : 0,
+                                                (e->flags & HVS_FLAG_MARGIN_AUDIT) ? e->d_audit.as<uint32_t>() : nullptr, out_ids,
                                                 out_dist, out_count);
     return cudaGetLastError();
 }
@@ -136,17 +167,17 @@ k_merge_partials(const float *__restrict__ queries, uint32_t m, uint32_t g, cons
     __syncthreads();
     for (uint32_t s = 0; s < g; ++s) {
         const size_t base = ((size_t)s * m + q) * K;
+        bool high = false;
         if (tid < K) {
             const uint32_t id = ids[base + tid];
             const float d = dist[base + tid];
-            if (id != 0xffffffffu && d < S.top.thr) S.top.push(d, id);
+            if (id != 0xffffffffu && d < S.top.thr) high = S.top.push(d, id) >= 1024u - 2u * K;
         }
         if (tid == 0) {
             const uint64_t t = (uint64_t)S.total + count[(size_t)s * m + q];
             S.total = t > 0xffffffffull ? 0xffffffffu : (uint32_t)t;
         }
-        __syncthreads();
-        if (S.top.cnt > 1024u - K) S.top.compact(tid, FT, 0.f, K);
+        if (__syncthreads_or(high)) S.top.compact(tid, FT, 0.f, K);   // block-uniform decision
     }
     __syncthreads();
     // candidates are (distance, global id) already: finish by hand (no arena lookup)
@@ -280,7 +311,8 @@ cudaError_t measure_ffma_peak(hvs_engine *e, uint32_t reps, float *tflops, float
     if (c != cudaSuccess) return c;
     const double flop = 2.0 * 256.0 * (double)iters * 256.0 * (double)blocks;
     *tflops = (float)(flop / ((double)best * 1e-3) / 1e12);
-    if (mhz) *mhz = (float)((double)cyc / ((double)best * 1e-3) / 1e6);
+    (void)cyc;   // the in-kernel cycle count is not a clock measurement (nvcc moves FFMAs across the clock reads)
+    if (mhz) *mhz = (float)((double)*tflops * 1e12 / ((double)e->sm_count * 128.0 * 2.0) / 1e6);   // the SM clock that rate implies
     return cudaSuccess;
 }
 

@@ -86,6 +86,26 @@ cudaError_t launch_plan_search(hvs_engine *e, const float *queries_dev, uint32_t
     return cudaGetLastError();
 }
 
+__global__ void k_gather_queries(const float *__restrict__ queries, const QSlice *__restrict__ slices,
+                                 const uint32_t *__restrict__ own, uint32_t n_own, float *__restrict__ q_sub, QSlice *__restrict__ sl_sub)
+{
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= n_own) return;
+    const uint32_t q = own[i];
+    const float4 *src = reinterpret_cast<const float4 *>(queries + (size_t)q * QROW);      // 416-byte rows: 16-byte aligned
+    float4 *dst = reinterpret_cast<float4 *>(q_sub + (size_t)i * QROW);
+    if (lane < QROW / 4) dst[lane] = src[lane];
+    if (lane == 31) sl_sub[i] = slices[q];
+}
+
+cudaError_t launch_gather_queries(hvs_engine *e, const float *queries_dev, const QSlice *slices_dev, const uint32_t *own_dev,
+                                  uint32_t n_own, float *q_sub, QSlice *sl_sub)
+{
+    if (!n_own) return cudaSuccess;
+    k_gather_queries<<<(unsigned)(((size_t)n_own * 32 + 255) / 256), 256, 0, e->stream>>>(queries_dev, slices_dev, own_dev, n_own, q_sub, sl_sub);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------
 // Host planner.
 //
@@ -93,7 +113,7 @@ cudaError_t launch_plan_search(hvs_engine *e, const float *queries_dev, uint32_t
 // cost is rows x 128 pair-slots whatever the queries need, while a direct scan costs exactly the rows
 // the query needs but runs at HBM speed (400 B per pair): a query takes the FFMA tile path when,
 // averaged over its slice, at least 128 / direct_cost_ratio other queries want the same rows.  On the
-// tensor kernel pair-slots are nearly free and the sweep is priced by the bytes of the bf16 image it
+// tensor kernel pair-slots are nearly free and the sweep is priced by the bytes of the fp16 image it
 // streams (224 B per row per <= 256 queries), so sharing the rows with about one other query is enough.
 // One solve never mixes the two tile kernels: their candidate thresholds are shared per query and
 // carry different error margins.
@@ -101,6 +121,22 @@ cudaError_t launch_plan_search(hvs_engine *e, const float *queries_dev, uint32_t
 // Everything is counting sorts over (chunk, query) incidences -- O(m log m + incidences), no
 // comparator sorts over the incidence list.
 namespace {
+// stable LSD radix sort of (64-bit key, payload) pairs, 11 bits per pass; digits that are the same everywhere are skipped
+void radix_sort_keys(std::vector<std::pair<uint64_t, uint32_t>> &keys)
+{
+    std::vector<std::pair<uint64_t, uint32_t>> tmp(keys.size());
+    uint64_t all_or = 0, all_and = ~0ull;
+    for (const auto &kv : keys) { all_or |= kv.first; all_and &= kv.first; }
+    for (int shift = 0; shift < 64; shift += 11) {
+        if ((((all_or ^ all_and) >> shift) & 0x7ffull) == 0) continue;
+        uint32_t hist[2049] = {0};
+        for (const auto &kv : keys) ++hist[((kv.first >> shift) & 0x7ffull) + 1];
+        for (int d = 0; d < 2048; ++d) hist[d + 1] += hist[d];
+        for (const auto &kv : keys) tmp[hist[(kv.first >> shift) & 0x7ffull]++] = kv;
+        keys.swap(tmp);
+    }
+}
+
 template <class F>
 void plan_parallel(unsigned nthreads, size_t njobs, F &&job)
 {
@@ -130,7 +166,7 @@ void plan_begin(const QSlice *sl, uint32_t m, const PlanParams &pp, Plan &P)
         uint32_t len = sl[i].end - sl[i].begin;
         P.pairs += len > (uint32_t)K ? len : (uint32_t)K;
     }
-    if (pp.mode != HVS_MODE_DIRECT) {
+    if (pp.mode != HVS_MODE_DIRECT && pp.approx_ok) {
         constexpr uint32_t CELL = 1024;
         const double need = tensor ? pp.tensor_min_depth : (double)QT / pp.direct_cost_ratio;
         for (uint32_t a = 0; a < 2; ++a) {
@@ -275,18 +311,7 @@ void plan_begin(const QSlice *sl, uint32_t m, const PlanParams &pp, Plan &P)
         std::vector<std::pair<uint64_t, uint32_t>> &keys = P.sort_keys[a];
         keys.resize(ord.size());
         for (size_t k = 0; k < ord.size(); ++k) keys[k] = {((uint64_t)sl[ord[k]].begin << 32) | sl[ord[k]].end, ord[k]};
-        // stable LSD radix sort on the 64-bit key (queries were collected in index order, so ties stay in index order)
-        std::vector<std::pair<uint64_t, uint32_t>> tmp(keys.size());
-        uint64_t all_or = 0, all_and = ~0ull;
-        for (const auto &kv : keys) { all_or |= kv.first; all_and &= kv.first; }
-        for (int shift = 0; shift < 64; shift += 11) {
-            if ((((all_or ^ all_and) >> shift) & 0x7ffull) == 0) continue;       // this digit is the same everywhere
-            uint32_t hist[2049] = {0};
-            for (const auto &kv : keys) ++hist[((kv.first >> shift) & 0x7ffull) + 1];
-            for (int d = 0; d < 2048; ++d) hist[d + 1] += hist[d];
-            for (const auto &kv : keys) tmp[hist[(kv.first >> shift) & 0x7ffull]++] = kv;
-            keys.swap(tmp);
-        }
+        radix_sort_keys(keys);
         for (size_t k = 0; k < ord.size(); ++k) ord[k] = keys[k].second;
     });
     lap("sort");
@@ -457,6 +482,52 @@ void plan_finish(const QSlice *sl, uint32_t m, Plan &P)
     });
 }
 
+// ------------------------------------------------------------------------------------------------
+// Query sharding over `world` engines (primary variant: D replicated, queries split; the reference's own
+// parallel variant splits D per query instead, include/optimized_parallel.hpp:100-146 / include/threading.hpp:116-118).
+//
+// What a rank's solve costs is the rows its queries sweep -- sum of slice lengths -- plus a fixed amount per query
+// (threshold warm-up, finalize), and the tile kernels live on queries that share rows being batched together.  So the
+// queries are ordered by (arena, begin, end) -- neighbours share rows -- and that sequence is cut, by cumulative cost,
+// into world x STRIPES contiguous segments that are dealt to the ranks round-robin: every rank gets the same cost AND
+// the same mix of query types (all-row sweeps, ranges, categories), while queries with equal or similar slices stay
+// together in runs.  Pure function of the slices: every rank computes the same answer without talking to the others.
+//   order  : all m query indices, rank-major (rank 0's queries first), each rank's in (arena, begin, end) order
+//   counts : queries per rank
+void shard_assign(const QSlice *sl, uint32_t m, uint32_t world, uint32_t *order, uint32_t *counts)
+{
+    if (world == 0) return;
+    for (uint32_t r = 0; r < world; ++r) counts[r] = 0;
+    if (!m) return;
+    std::vector<std::pair<uint64_t, uint32_t>> keys[2];
+    for (uint32_t i = 0; i < m; ++i) keys[sl[i].arena & 1u].push_back({((uint64_t)sl[i].begin << 32) | sl[i].end, i});
+    radix_sort_keys(keys[0]);
+    radix_sort_keys(keys[1]);
+    auto cost_of = [&](uint32_t i) { return (uint64_t)std::max(sl[i].end - sl[i].begin, (uint32_t)K) + SHARD_QUERY_COST; };
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < m; ++i) total += cost_of(i);
+    uint32_t stripes = SHARD_STRIPES;
+    while (stripes > 1 && (uint64_t)world * stripes * 64 > m) stripes >>= 1;      // small batches: fewer, longer runs
+    const uint64_t nseg = (uint64_t)world * stripes;
+    std::vector<uint8_t> owner(m);
+    uint64_t cum = 0;
+    for (int a = 0; a < 2; ++a)
+        for (const auto &kv : keys[a]) {
+            const uint64_t c = cost_of(kv.second);
+            // the segment that holds the midpoint of this query's cost interval
+            unsigned __int128 pos = (unsigned __int128)(cum + c / 2) * nseg;
+            uint64_t seg = (uint64_t)(pos / total);
+            if (seg >= nseg) seg = nseg - 1;
+            owner[kv.second] = (uint8_t)(seg % world);
+            cum += c;
+        }
+    for (uint32_t i = 0; i < m; ++i) ++counts[owner[i]];
+    std::vector<uint32_t> off(world + 1, 0);
+    for (uint32_t r = 0; r < world; ++r) off[r + 1] = off[r] + counts[r];
+    for (int a = 0; a < 2; ++a)
+        for (const auto &kv : keys[a]) order[off[owner[kv.second]]++] = kv.second;
+}
+
 void plan_build(const QSlice *sl, uint32_t m, const PlanParams &pp, Plan &P)
 {
     plan_begin(sl, m, pp, P);
@@ -495,4 +566,17 @@ extern "C" int hvs_plan_dryrun(const uint32_t *arena, const uint32_t *begin, con
         }
     if (out_pairs_computed) *out_pairs_computed = P.pairs_computed;
     return (int)P.items.size();
+}
+
+extern "C" int hvs_shard_assign_host(const uint32_t *arena, const uint32_t *begin, const uint32_t *end, uint32_t m,
+                                     uint32_t world, uint32_t *out_order, uint32_t *out_counts)
+{
+    if (!world || world > 255 || !out_counts || (m && (!arena || !begin || !end || !out_order))) return HVS_ERR_INVALID;
+    std::vector<hvs::QSlice> sl(m);
+    for (uint32_t i = 0; i < m; ++i) {
+        if (arena[i] > 1 || end[i] < begin[i]) return HVS_ERR_INVALID;
+        sl[i].arena = arena[i]; sl[i].begin = begin[i]; sl[i].end = end[i]; sl[i].qnorm = 0.f;
+    }
+    hvs::shard_assign(sl.data(), m, world, out_order, out_counts);
+    return HVS_OK;
 }

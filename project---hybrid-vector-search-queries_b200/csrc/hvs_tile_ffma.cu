@@ -260,19 +260,17 @@ k_tile_ffma(const float *__restrict__ queries, const QSlice *__restrict__ slices
     if ((uint32_t)tid < it.nq) cand_cnt[it.out_off + tid] = S.lcnt[tid];
 }
 
+cudaError_t tile_ffma_init_attributes()
+{
+    return cudaFuncSetAttribute(k_tile_ffma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem));
+}
+
 cudaError_t launch_tile_ffma(hvs_engine *e, const float *queries_dev, const QSlice *slices_dev, const TileItem *items_dev,
                              uint32_t item_begin, uint32_t n_items, const uint32_t *item_q_dev, uint64_t *cand_dev,
                              uint32_t *cand_cnt_dev, uint32_t *gthr_dev, uint32_t *flags_dev, float margin_scale)
 {
     if (!n_items) return cudaSuccess;
-    static bool attr_done_dev[64] = {false};                  // the attribute is per device
-    bool &attr_done = attr_done_dev[e->device & 63];
     const int smem = (int)sizeof(TileSmem);
-    if (!attr_done) {
-        cudaError_t c = cudaFuncSetAttribute(k_tile_ffma, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (c != cudaSuccess) return c;
-        attr_done = true;
-    }
     const Index &ix = e->index;
     k_tile_ffma<<<n_items, NT, smem, e->stream>>>(queries_dev, slices_dev, items_dev + item_begin, item_q_dev, ix.arena(0),
                                                    ix.arena(1), ix.n, ix.xnorm_max, margin_scale, cand_dev, cand_cnt_dev,

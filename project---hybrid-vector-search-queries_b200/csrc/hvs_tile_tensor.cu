@@ -450,7 +450,13 @@ __global__ void k_build_image(const float *__restrict__ x, const float *__restri
     if (i >= (size_t)n_img * KU) return;
     const uint32_t row = (uint32_t)(i / KU), u = (uint32_t)(i % KU);
     float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (row < n) {
+    // norm outliers (K0 set their ||x||^2 to +inf): a zero vector with the largest norm term fp16 holds -- the score is
+    // 60000 for every query, far above any inlier's (<= 32000 + 2 * 60000 / 2 ... see margin_tensor), so they never
+    // crowd a pool; K5 scores them exactly whatever happens here
+    const bool outlier = row < n && !(xnorm[row] < __int_as_float(0x7f800000));
+    if (outlier) {
+        if (u == 12) v[4] = 60000.f;
+    } else if (row < n) {
         if (u < 12) {
             const float4 a = *reinterpret_cast<const float4 *>(x + (size_t)row * DIM + 8 * u);
             const float4 b = *reinterpret_cast<const float4 *>(x + (size_t)row * DIM + 8 * u + 4);
@@ -476,17 +482,17 @@ __global__ void k_build_image(const float *__restrict__ x, const float *__restri
     *reinterpret_cast<uint4 *>(img + (size_t)(row >> 3) * GROUP_B + u * 128 + (row & 7) * 16) = *reinterpret_cast<uint4 *>(p);
 }
 
-void build_tensor_image(hvs_engine *e, int a)
+cudaError_t build_tensor_image(hvs_engine *e, int a)
 {
     Index &ix = e->index;
     const uint32_t n_img = ((ix.n + 7u) & ~7u) + 2 * TN;        // every stage copy stays inside the image
-    if (ix.xb[a].ensure((size_t)n_img * ROW_B) != cudaSuccess) { cudaGetLastError(); ix.xb[a].release(); return; }
+    cudaError_t c = ix.xb[a].ensure((size_t)n_img * ROW_B);
+    if (c != cudaSuccess) return c;
     const size_t total = (size_t)n_img * KU;
     k_build_image<<<(unsigned)((total + 255) / 256), 256, 0, e->stream>>>(ix.x[a].as<float>(), ix.xnorm[a].as<float>(), ix.n, n_img,
                                                                           ix.img_scale, ix.xb[a].as<unsigned char>());
+    return cudaGetLastError();
 }
-
-bool tensor_path_available() { return true; }
 
 // ---- the sweep --------------------------------------------------------------------------------------
 template <bool PIPE>
@@ -847,20 +853,19 @@ cudaError_t tile_tensor_begin(hvs_engine *e)
     return cudaSuccess;
 }
 
+cudaError_t tile_tensor_init_attributes()
+{
+    cudaError_t c = cudaFuncSetAttribute(k_tile_tensor<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TensorSmem));
+    if (c == cudaSuccess) c = cudaFuncSetAttribute(k_tile_tensor<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TensorSmem));
+    return c;
+}
+
 cudaError_t launch_tile_tensor(hvs_engine *e, const float *queries_dev, const QSlice *slices_dev, const TileItem *items_dev,
                                uint32_t item_begin, uint32_t n_items, const uint32_t *item_q_dev, uint64_t *cand_dev,
                                uint32_t *cand_cnt_dev, uint32_t *gthr_dev, uint32_t *flags_dev)
 {
     if (!n_items) return cudaSuccess;
-    static bool attr_done_dev[64] = {false};                  // the attribute is per device (one engine per GPU, maybe several per process)
-    bool &attr_done = attr_done_dev[e->device & 63];
     const int smem = (int)sizeof(TensorSmem);
-    if (!attr_done) {
-        cudaError_t c = cudaFuncSetAttribute(k_tile_tensor<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (c == cudaSuccess) c = cudaFuncSetAttribute(k_tile_tensor<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (c != cudaSuccess) return c;
-        attr_done = true;
-    }
     const Index &ix = e->index;
     const uint32_t grid = n_items < (uint32_t)e->sm_count ? n_items : (uint32_t)e->sm_count;
     cudaError_t c = cudaSuccess;

@@ -196,14 +196,19 @@ struct TopBuf {
     {
         return ORD ? okey_inv((uint32_t)(k >> 32)) : __uint_as_float((uint32_t)(k >> 32));
     }
-    __device__ __forceinline__ void push(float d, uint32_t payload)
+    // Returns the slot the entry took.  Callers decide about a compaction from the slots their own pushes got
+    // (cnt > L  <=>  some push of this round got slot >= L), combined with __syncthreads_or: reading `cnt` after
+    // the barrier would race with threads that already push the next round.
+    __device__ __forceinline__ uint32_t push(float d, uint32_t payload)
     {
         uint32_t slot = atomicAdd(&cnt, 1u);
         if (slot < (uint32_t)CAP) cand[slot] = ORD ? (((uint64_t)okey(d) << 32) | payload) : pack_key(d, payload);
+        return slot;
     }
     // Call from ALL threads after a __syncthreads().  Keeps <= keep_max entries.
     __device__ __forceinline__ void compact(int tid, int nthreads, float margin, int keep_max)
     {
+        static_assert((CAP & (CAP - 1)) == 0, "the bitonic sort pads to the next power of two, which must fit the buffer");
         int c = min((int)cnt, CAP);
         int n = next_pow2(c < 2 ? 2 : c);
         for (int i = c + tid; i < n; i += nthreads) cand[i] = KEY_INF;
@@ -305,12 +310,14 @@ struct TopBuf {
 // apply the pad rule, sort, write.
 template <int CAP, bool ORD>
 __device__ __forceinline__ void finish_query(TopBuf<CAP, ORD> &top, const float *q_smem, const Arena &A, uint32_t len,
-                                             const float *__restrict__ tail, uint32_t n_total, uint32_t q, bool partial,
+                                             const float *__restrict__ tail, uint32_t n_total, uint32_t id_offset, uint32_t q, bool partial,
                                              uint32_t *__restrict__ out_ids, float *__restrict__ out_dist,
                                              uint32_t *__restrict__ out_count, int tid, int nthreads)
 {
-    // keep the best K by (dist, pos), then re-key by original id so the output order is
-    // (dist, id) -- deterministic whatever path produced the candidates
+    // keep the best K by (dist, arena position), then re-key by original id: the output is ordered by (dist, id);
+    // WHICH rows survive among exactly equal distances at the 100-th place is decided by arena position (and, in
+    // the streaming kernels, by when a compaction ran) -- like the reference, whose tie order is unspecified
+    // (unstable std::sort, include/baseline.hpp:159-166)
     if ((int)top.cnt > K) top.compact(tid, nthreads, 0.f, K);
     int c = min((int)top.cnt, K);
     for (int i = tid; i < c; i += nthreads) {
@@ -324,7 +331,7 @@ __device__ __forceinline__ void finish_query(TopBuf<CAP, ORD> &top, const float 
         int npad = K - (int)len;
         for (int s = tid; s < npad; s += nthreads) {
             float d = ref_dist_row(tail + (size_t)s * DIM, q_smem);
-            top.cand[c + s] = pack_key(d, n_total - 1u - (uint32_t)s);
+            top.cand[c + s] = pack_key(d, n_total - 1u - (uint32_t)s + id_offset);   // same id space as A.ids (k_gather adds id_offset)
         }
         c += npad;
     }

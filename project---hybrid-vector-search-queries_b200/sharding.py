@@ -2,8 +2,9 @@
 
 Two ways to use G GPUs for the solve step:
 
-* query-sharded (primary): D is replicated, rank r solves queries [lo, hi) of `query_shard`; every
-  rank writes its own rows of the result -- no collective on the data path.
+* query-sharded (primary): D is replicated; `solve_sharded` has every rank solve its share of ONE batch
+  (hvs_solve_shard_device: shares balanced by the rows the queries sweep, queries that share rows kept on one rank)
+  and combines the rows with a single all-gather -- the only exchange, 400 bytes per query.
 * data-sharded (comparison; the reference's own strategy, include/optimized_parallel.hpp:100-157, at
   GPU scale): rank r indexes rows `data_shard(n, r, G)` with id_offset = lo and produces, per query,
   its local best <= 100 (distance, global id) pairs plus the local match count
@@ -63,3 +64,45 @@ def gather_query_results(ids_local, m: int, world: int):
         parts.append(out[r, : hi - lo])
     del rank
     return torch.cat(parts, 0)
+
+
+def scatter_index(order, counts):
+    """For the all-gather of `solve_sharded`: where row j of the padded [world, longest, 100] gather goes.
+    -> (src[m] flat row index into the gathered block, dst[m] query index), both int64 numpy arrays."""
+    import numpy as np
+    counts = np.asarray(counts, np.int64)
+    longest = int(counts.max()) if counts.size else 0
+    src = np.concatenate([r * longest + np.arange(c, dtype=np.int64) for r, c in enumerate(counts)]) if counts.size else np.zeros(0, np.int64)
+    return src, np.asarray(order, np.int64), longest
+
+
+def solve_sharded(engine, queries_dev, rank: int, world: int, scratch=None):
+    """One batch, `world` ranks (torch.distributed initialised, one process per GPU, D indexed on every rank):
+    every rank solves its share (hvs_solve_shard_device) and ONE all_gather_into_tensor brings the rows together;
+    returns the [m, 100] int32 ids in query order, on every rank.  `scratch` (a dict, optional) keeps the device
+    buffers between calls."""
+    import torch
+    import torch.distributed as td
+    m = queries_dev.shape[0]
+    sc = scratch if scratch is not None else {}
+    dev = queries_dev.device
+    if sc.get("m") != m or sc.get("world") != world:
+        sc.clear()
+        sc.update(m=m, world=world, own=torch.empty((m, 100), dtype=torch.int32, device=dev),
+                  out=torch.empty((m, 100), dtype=torch.int32, device=dev))
+    order, counts = engine.solve_shard_device(queries_dev, rank, world, sc["own"])
+    if world == 1:
+        sc["out"].index_copy_(0, torch.from_numpy(order.astype("int64")).to(dev), sc["own"])
+        return sc["out"]
+    src, dst, longest = scatter_index(order, counts)
+    if sc.get("cap", -1) < longest:                        # rows every rank contributes to the gather (same on all ranks)
+        sc["cap"] = min(m, longest + longest // 8 + 8)
+        sc["gath"] = torch.empty((world * sc["cap"], 100), dtype=torch.int32, device=dev)
+    cap = sc["cap"]
+    if cap != longest and longest:                         # the gather block is sized with slack: re-derive the row positions
+        src = (src // longest) * cap + (src % longest)
+    td.all_gather_into_tensor(sc["gath"], sc["own"][:cap])
+    idx = torch.from_numpy(src).to(dev, non_blocking=True)
+    to = torch.from_numpy(dst).to(dev, non_blocking=True)
+    sc["out"].index_copy_(0, to, sc["gath"].index_select(0, idx))
+    return sc["out"]

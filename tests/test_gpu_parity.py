@@ -343,3 +343,89 @@ def test_skewed_categories_and_clustered_vectors(H, oracle, check, datagen, zipf
     for tag, mode in modes(H):
         ids, st, dd = solve(H, d, q, mode)
         assert_parity(check, oracle, d, q, ref, ids, dd, f"zipf={zipf} clusters={clusters}/{tag}")
+
+
+# ---- the candidate margins under adversarial inputs ---------------------------------------------
+def _audit_solve(H, d, q, mode):
+    with H.Engine(mode=mode, flags=H.FLAG_MARGIN_AUDIT) as e:
+        e.index_build(d)
+        ids = e.solve(q)
+        return ids, e.stats(), e.rescore(q, ids)
+
+
+def test_margin_audit_regular_data(H, oracle, check, datagen):
+    """The error bound behind the margins (hvs_margin.cuh), measured on the device: over every re-ranked survivor
+    |approximate score + ||q||^2 - reference distance| must stay below the eps the margins assume."""
+    d = datagen.gen_data(80_000, 91, ncat=4)
+    q = datagen.gen_queries(512, 92, ncat=4)
+    ref = oracle.vec_query(d, q[:96], want_dist=False)
+    for tag, mode in (("exact", H.MODE_EXACT), ("auto", H.MODE_AUTO)):
+        ids, st, dd = _audit_solve(H, d, q, mode)
+        assert st["n_tile"] > 0 and 0.0 < st["margin_audit"] < 1.0, (tag, st)
+        p = check.compare(d, q[:96], ref, ids[:96], rtol=RTOL)
+        assert p.ok and p.dist_bit_identical_rows == 96, f"{tag}: {p.summary()}"
+
+
+def test_norm_outlier_rows(H, oracle, check, datagen):
+    """One row with 10^3 x the norm of the rest (and a few more, and a non-finite one) must neither wreck the fp16 scale
+    nor push every query onto the exact fallback: the index sets such rows aside, K5 scores them exactly -- also when an
+    outlier IS among a query's nearest rows."""
+    n, m = 70_000, 300
+    d = datagen.gen_data(n, 93, ncat=3)
+    rng = np.random.default_rng(94)
+    big = rng.choice(n - 200, 7, replace=False)
+    d[big, 2:] *= 1000.0
+    d[big[0], 2:] *= 1000.0                                   # 10^6 x: ||x||^2 ~ 10^15
+    q = datagen.gen_queries(m, 95, ncat=3)
+    q[:8, 4:] = d[big[:4].repeat(2), 2:] * np.float32(0.999)  # queries right next to outliers
+    q[:8, 0] = [0, 0, 2, 2, 1, 1, 3, 3]
+    q[:8, 1] = d[big[:4].repeat(2), 0]
+    q[:8, 2], q[:8, 3] = -3.0, 3.0
+    ref = oracle.vec_query(d, q, want_dist=False)
+    assert any(big[0] in ref[i] for i in range(8))            # the outlier really is an answer
+    for tag, mode in modes(H):
+        ids, st, dd = _audit_solve(H, d, q, mode)
+        assert_parity(check, oracle, d, q, ref, ids, dd, f"outliers/{tag}")
+        if mode != H.MODE_DIRECT:
+            assert st["n_outliers"] == 7 and st["n_tile"] > 0, st
+            # the 8 queries with a huge norm may take the fallback (their own -2 sx q leaves fp16); nobody else does
+            assert st["n_fallback"] <= 8 and st["margin_audit"] < 1.0, (tag, st)
+
+
+def test_tiny_and_huge_scales(H, oracle, check, datagen):
+    """All-tiny norms (fp16 would flush to subnormals without the power-of-two image scale), all-huge norms, and a
+    query whose scaled norm leaves fp16's range (the `flags` path of K3: that query alone takes the exact scan)."""
+    n, m = 50_000, 200
+    base = datagen.gen_data(n, 96, ncat=3)
+    qb = datagen.gen_queries(m, 97, ncat=3)
+    for scale in (1e-4, 3e3):
+        d, q = base.copy(), qb.copy()
+        d[:, 2:] *= np.float32(scale)
+        q[:, 4:] *= np.float32(scale)
+        if scale > 1:
+            q[5, 4:] *= np.float32(500.0)                     # 2 sx ||q|| > 60000
+        ref = oracle.vec_query(d, q, want_dist=False)
+        for tag, mode in modes(H):
+            ids, st, dd = _audit_solve(H, d, q, mode)
+            assert_parity(check, oracle, d, q, ref, ids, dd, f"scale={scale}/{tag}")
+            if mode == H.MODE_AUTO:
+                assert st["n_items_tensor"] > 0 and st["margin_audit"] < 1.0, st
+                assert st["n_fallback"] <= (1 if scale > 1 else 0), st
+
+
+def test_id_offset_with_pad_rows(H, oracle, check, datagen):
+    """A shard engine (id_offset != 0) used through the non-partial entry points: pad ids carry the offset like real
+    matches do, and hvs_rescore maps both back."""
+    n, off = 20_000, 1_000_000
+    d = datagen.gen_data(n, 98, ncat=500)
+    q = datagen.gen_queries(120, 99, ncat=500, types=(1, 3))     # tiny categories: the pad rule on most queries
+    ref = oracle.vec_query(d, q, want_dist=False)
+    with H.Engine(mode=H.MODE_AUTO, id_offset=off) as e:
+        e.index_build(d)
+        ids = e.solve(q)
+        dist = e.rescore(q, ids)
+    assert ids.min() >= off
+    local = (ids - np.uint32(off)).astype(np.uint32)
+    p = check.compare(d, q, ref, local, rtol=RTOL)
+    assert p.ok and p.dist_bit_identical_rows == len(q), p.summary()
+    assert np.array_equal(dist.view(np.uint32), oracle.rescore(d, q, local).view(np.uint32))

@@ -30,7 +30,7 @@ def test_header_symbols_exported(H):
 
 def test_struct_layouts_match_header(H):
     assert ctypes.sizeof(H.Config) == 32
-    assert ctypes.sizeof(H.Stats) == 128
+    assert ctypes.sizeof(H.Stats) == 136
 
 
 def test_no_cpu_fallback(H):

@@ -127,3 +127,116 @@ def test_data_sharded_gather_and_merge_world2(tmp_path, oracle, check):
     p = check.compare(d, q, ref, got)
     assert p.ok and p.dist_bit_identical_rows == m, p.summary()
     assert np.array_equal(r0["allq"][:, 0], np.arange(m))          # query-sharded blocks come back in query order
+
+
+# ---- query-sharded solve of ONE batch (strong scaling): assignment + the single all-gather ---------------------------
+def _headline_like_slices(m, n, ncat, seed):
+    """Slices shaped like BASELINE configs[2]: a quarter each of all-row sweeps, T ranges, categories, category ranges."""
+    rng = np.random.default_rng(seed)
+    t = rng.integers(0, 4, m)
+    arena = np.where((t == 1) | (t == 3), 1, 0).astype(np.uint32)
+    begin = np.zeros(m, np.uint32)
+    end = np.full(m, n, np.uint32)
+    lo = rng.random(m)
+    hi = lo + rng.random(m) * (1.0 - lo)
+    r2 = t == 2
+    begin[r2] = (lo[r2] * n).astype(np.uint32)
+    end[r2] = np.maximum((hi[r2] * n).astype(np.uint32), begin[r2])
+    cat = rng.integers(0, ncat, m)
+    clen = n // ncat
+    c1 = t == 1
+    begin[c1] = cat[c1] * clen
+    end[c1] = (cat[c1] + 1) * clen
+    c3 = t == 3
+    begin[c3] = (cat[c3] * clen + lo[c3] * clen).astype(np.uint32)
+    end[c3] = np.maximum((cat[c3] * clen + hi[c3] * clen).astype(np.uint32), begin[c3])
+    return t, arena, begin, end, cat
+
+
+def test_shard_assign_balance_locality_determinism(hvs):
+    n, m, ncat = 10_000_000, 40_000, 100
+    t, arena, begin, end, cat = _headline_like_slices(m, n, ncat, 7)
+    cost = np.maximum(end - begin, 100).astype(np.int64) + 400_000
+    for world in (1, 2, 4, 8):
+        order, counts = hvs.shard_assign(arena, begin, end, world)
+        order2, counts2 = hvs.shard_assign(arena, begin, end, world)
+        assert np.array_equal(order, order2) and np.array_equal(counts, counts2)          # a pure function of the slices
+        assert int(counts.sum()) == m and sorted(order.tolist()) == list(range(m))      # every query exactly once
+        owner = np.empty(m, np.int64)
+        off = 0
+        for r in range(world):
+            owner[order[off:off + counts[r]]] = r
+            off += int(counts[r])
+        per = np.array([cost[owner == r].sum() for r in range(world)], np.float64)
+        assert per.max() / per.mean() < 1.03, (world, per / per.mean())                   # balanced by rows swept
+        if world > 1:
+            # every rank gets the same mix: all-row sweeps split evenly, and ranges, and category queries
+            for typ in range(4):
+                share = np.array([(t[owner == r] == typ).sum() for r in range(world)], np.float64)
+                assert share.min() > 0 and share.max() / share.mean() < 1.6, (world, typ, share)
+            # queries of one category stay on few ranks (they share rows: the tile kernels batch them)
+            spread = [len(set(owner[(t == 1) & (cat == c)].tolist())) for c in range(ncat)]
+            assert np.mean(spread) <= 2.0, np.mean(spread)
+            # each rank's queries come in (arena, begin, end) order
+            off = 0
+            for r in range(world):
+                o = order[off:off + counts[r]]
+                key = (arena[o].astype(np.uint64) << np.uint64(63)) | (begin[o].astype(np.uint64) << np.uint64(31)) | (end[o].astype(np.uint64) >> np.uint64(1))
+                assert (np.diff(key.astype(np.float64)) >= 0).all()
+                off += int(counts[r])
+    for bad in (0, 256):
+        with pytest.raises(hvs.HvsError):
+            hvs.shard_assign(arena[:10], begin[:10], end[:10], bad)
+    order, counts = hvs.shard_assign(arena[:0], begin[:0], end[:0], 4)
+    assert counts.tolist() == [0, 0, 0, 0]
+    order, counts = hvs.shard_assign(arena[:3], begin[:3], end[:3], 8)                      # fewer queries than ranks
+    assert int(counts.sum()) == 3
+
+
+class _StubEngine:
+    """Stands in for Engine.solve_shard_device on the CPU: the assignment is the product's own (hvs_shard_assign_host),
+    the 'answer' of query i is the row [i, i+1, ..., i+99] so that any misplaced row shows."""
+
+    def __init__(self, hvs, arena, begin, end):
+        self.hvs, self.sl = hvs, (arena, begin, end)
+
+    def solve_shard_device(self, q, rank, world, out):
+        import torch
+        order, counts = self.hvs.shard_assign(*self.sl, world)
+        off = int(counts[:rank].sum())
+        own = order[off:off + int(counts[rank])].astype(np.int64)
+        out[: len(own)] = torch.from_numpy(own[:, None] + np.arange(100)[None, :]).to(torch.int32)
+        out[len(own):] = -7                                 # stale rows beyond the rank's share must never be picked up
+        return order, counts
+
+
+def _worker_sharded(rank, world, port, m, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as td
+    hvs = importlib.import_module(PKG)
+    sh = importlib.import_module(PKG + ".sharding")
+    td.init_process_group("gloo", rank=rank, world_size=world)
+    res = []
+    scratch = {}
+    for mm, seed in ((m, 1), (m, 2), (m // 3, 3), (2 * m, 4)):           # changing batch sizes re-size the gather block
+        _, arena, begin, end, _ = _headline_like_slices(mm, 1_000_000, 10, seed)
+        eng = _StubEngine(hvs, arena, begin, end)
+        q = torch.zeros((mm, 104), dtype=torch.float32)
+        out = sh.solve_sharded(eng, q, rank, world, scratch)
+        res.append(out.numpy().copy())
+    np.savez(os.path.join(out_dir, f"s{rank}.npz"), *res)
+    td.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_solve_sharded_gather_world2(tmp_path, hvs):
+    import torch.multiprocessing as mp
+    m, world = 900, 2
+    port = _free_port()
+    mp.spawn(_worker_sharded, args=(world, port, m, str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = np.load(tmp_path / "s0.npz"), np.load(tmp_path / "s1.npz")
+    for k, mm in zip(r0.files, (m, m, m // 3, 2 * m)):
+        want = np.arange(mm)[:, None] + np.arange(100)[None, :]
+        assert np.array_equal(r0[k], want) and np.array_equal(r1[k], want), k      # query order, on every rank
