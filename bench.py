@@ -1,17 +1,23 @@
 #!/usr/bin/env python
 """bench.py -- queries/sec of the filtered k-NN solve step (BASELINE.json metric).
 
-A "step" is one pass of the hot path -- hvs_solve over the whole query batch -- against an index
-that was built once before the timed region (the contest's indexing phase never sees queries).
-  value : queries/s with the query batch already resident in HBM (hvs_solve_device), CUDA events
-          on the engine's stream (which is torch's current stream), max over ranks.
-  e2e   : the same through the host entry point hvs_solve: pinned host queries -> H2D -> solve ->
-          D2H of the uint32 ids, every step.
-Workload at N=1: BASELINE.json configs[2], D=10^7, Q=4x10^4 mixed types 0-3 (synthetic, the repo's
-seedable generator with the reference generators' value ranges and integer categories).
-N>1: query-sharded, D replicated, no data-path collective: each rank solves its own Q-sized batch
-(weak scaling).  `--variant data` runs the data-sharded comparison (NCCL all-gather + K5 merge).
+A "step" is one pass of the hot path -- the solve of the whole query batch -- against an index that was
+built once before the timed region (the contest's indexing phase never sees queries).
+  value : queries/s with the query batch already resident in HBM, CUDA events on the engine's stream
+          (an explicit torch stream whose handle the engine was created on), max over ranks.
+  e2e   : the same through the host-facing call: pinned host queries -> H2D -> solve -> D2H of the
+          uint32 ids, every step.
+Workload: BASELINE.json configs[2], D=10^7, Q=4x10^4 mixed types 0-3 (synthetic, the repo's seedable
+generator with the reference generators' value ranges and integer categories).
+N=1  : hvs_solve_device / hvs_solve.  After the headline the same process runs EXACT mode on the same batch and
+       AUTO mode on BASELINE.json configs[0,1,3,4] (few steps each) and reports them under "configs".
+N>1  : ONE batch of Q=4x10^4 queries, query-sharded over the ranks inside the product
+       (hvs_solve_shard_device + one NCCL all-gather: sharding.solve_sharded), D replicated: STRONG scaling.
+       A weak-scaling figure (every rank its own batch, no exchange) is reported beside it.
+       `--variant data` runs the data-sharded comparison (NCCL all-gather of partial top-100s + K5 merge).
 `--impl reference` times the reference's own CPU vec_query (oracle/_ref) on a bounded sample.
+Parity (outside the timed regions, the oracle is the checker only): AUTO vs EXACT over all queries,
+>= 256 queries against the reference's optimized_parallel build, >= 16 against baseline.hpp -- at every N.
 """
 from __future__ import annotations
 
@@ -23,6 +29,7 @@ import subprocess
 import sys
 import tempfile
 import time
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -38,7 +45,7 @@ WORKLOADS = {
     "type0": (10_000_000, 40_000, 100, (0,), None),                  # configs[3]
     "selective": (10_000_000, 40_000, 1000, (3,), 0.06),             # configs[4]
 }
-DATA_SEED, QUERY_SEED = 3, 4
+DATA_SEED, QUERY_SEED, RECAT_SEED = 3, 4, 5
 
 
 def parse():
@@ -51,16 +58,31 @@ def parse():
     ap.add_argument("--mode", default="auto", choices=["auto", "exact", "direct", "tensor"])
     ap.add_argument("--variant", default="query", choices=["query", "data"], help="multi-GPU sharding")
     ap.add_argument("--cpu-sample", type=int, default=32, help="queries of the workload timed on the CPU baseline")
+    ap.add_argument("--parity-sample", type=int, default=256, help="queries checked against the reference's parallel build")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="N=1: skip the EXACT / other-config runs after the headline")
     return ap.parse_args()
 
 
-def make_inputs(hvs, wl, rank=0):
+def recategorise(d, ncat):
+    """configs[4] data = the large workload's rows (same T, same vectors) with the category column redrawn from
+    `ncat` integer categories (in place: a second 4 GB array would double the host footprint)."""
+    rng = np.random.default_rng(RECAT_SEED)
+    d[:, 0] = np.floor(rng.random(d.shape[0], dtype=np.float32) * np.float32(ncat))
+    return d
+
+
+def make_data(hvs, wl):
     n, m, ncat, types, rw = WORKLOADS[wl]
-    d = hvs.gen_data(n, DATA_SEED, ncat=ncat)
-    q = hvs.gen_queries(m, QUERY_SEED + 1000 * rank, ncat=ncat, types=types, range_width=rw)
-    return d, q
+    if wl == "selective":
+        return recategorise(hvs.gen_data(n, DATA_SEED, ncat=100), ncat)
+    return hvs.gen_data(n, DATA_SEED, ncat=ncat)
+
+
+def make_queries(hvs, wl, salt=0):
+    n, m, ncat, types, rw = WORKLOADS[wl]
+    return hvs.gen_queries(m, QUERY_SEED + 1000 * salt, ncat=ncat, types=types, range_width=rw)
 
 
 # ---- clocks -----------------------------------------------------------------------------------
@@ -121,10 +143,11 @@ def cpu_reference_run(d, q_sample, steps, warmup):
         if not O.ref_available(impl):
             continue
         ts = []
-        for s in range(warmup + steps):
-            _, secs = O.ref_vec_query(impl, d, q_sample)
-            if s >= warmup:
-                ts.append(secs)
+        with O.RefSession(impl, d) as rs:                 # D is converted to the reference's nested vectors once, outside the timing
+            for s in range(warmup + steps):
+                _, secs = rs.query(q_sample)
+                if s >= warmup:
+                    ts.append(secs)
         out[impl] = {"kind": kind, "desc": desc, "secs": float(np.mean(ts)), "threads": min(cores, max(1, d.shape[0] // 100_000))}
         if impl == "parallel_nodbg":
             break           # the as-shipped build is strictly slower; time it only if the fair one is absent
@@ -142,7 +165,8 @@ def cpu_reference_run(d, q_sample, steps, warmup):
         t = q_sample[:, 0].astype(int)
         pick = [int(np.nonzero(t == k)[0][0]) for k in sorted(set(t.tolist()))][:4]
         qb = np.ascontiguousarray(q_sample[pick])
-        _, secs = O.ref_vec_query("baseline", d, qb)
+        with O.RefSession("baseline", d) as rs:
+            _, secs = rs.query(qb)
         out["baseline"] = {"kind": "reference", "desc": "baseline.hpp (IMPL=1), one thread", "secs": float(secs), "threads": 1,
                            "queries": len(pick)}
     return best, out
@@ -154,20 +178,31 @@ def sample_queries(q, k):
     return np.ascontiguousarray(q[idx]), idx
 
 
+def cpu_baseline_entry(d, q, k):
+    qs, _ = sample_queries(q, k)
+    best, allv = cpu_reference_run(d, qs, 1, 0)
+    m, n = q.shape[0], d.shape[0]
+    return {"value": qs.shape[0] / best["secs"], "unit": "queries/s", "cores": best["threads"], "kind": best["kind"],
+            "sample": f"{qs.shape[0]} of the {m} queries (every {m // max(1, qs.shape[0])}-th, same type mix) against the "
+                      f"full D={n}, one pass; {best['desc']}; host has {os.cpu_count()} cores",
+            "variants": {k2: {"queries_per_s": v.get("queries", qs.shape[0]) / v["secs"], "threads": v["threads"],
+                              "what": v["desc"]} for k2, v in allv.items()}}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
     hvs_dg = importlib.import_module(PKG + ".datagen")
     n, m, ncat, types, rw = WORKLOADS[args.workload]
-    d = hvs_dg.gen_data(n, DATA_SEED, ncat=ncat)
-    q = hvs_dg.gen_queries(m, QUERY_SEED, ncat=ncat, types=types, range_width=rw)
+    d = make_data(hvs_dg, args.workload)
+    q = make_queries(hvs_dg, args.workload)
     qs, _ = sample_queries(q, args.cpu_sample)
     best, allv = cpu_reference_run(d, qs, args.steps, args.warmup)
     qps = qs.shape[0] / best["secs"]
     line = {"impl": "reference", "metric": "queries/sec", "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": best["secs"] * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, 1),
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.workload, args.mode, 1, args.variant),
             "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": best["threads"], "kind": best["kind"],
                              "sample": f"{qs.shape[0]} of the workload's {m} queries (every {m // max(1, qs.shape[0])}-th, same type mix) "
                                        f"against the full D={n}; {best['desc']}; host has {os.cpu_count()} cores",
@@ -177,13 +212,177 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, world):
-    n, m, ncat, types, rw = WORKLOADS[args.workload]
-    return {"workload": f"{args.workload}: D={n} rows x 100-d f32, Q={m} queries per GPU, k=100, types {list(types)} uniform, "
+def workload_config(wl, mode, world, variant="query"):
+    n, m, ncat, types, rw = WORKLOADS[wl]
+    if world == 1:
+        sh = "single GPU"
+    elif variant == "query":
+        sh = f"ONE batch of {m} queries sharded over {world} GPUs by rows swept (hvs_solve_shard_device), D replicated, one NCCL all-gather of the ids"
+    else:
+        sh = f"data-sharded: {world} GPUs hold N/{world} rows each, the same {m} queries, NCCL all-gather of partial top-100s + K5 merge"
+    return {"workload": f"{wl}: D={n} rows x 100-d f32, Q={m} queries in total, k=100, types {list(types)} uniform, "
                         f"{ncat} integer categories" + (f", range width {rw}" if rw else ""),
-            "D": n, "Q_per_gpu": m, "k": 100, "dim": 100, "ncat": ncat, "types": list(types), "mode": args.mode,
-            "sharding": ("query-sharded, D replicated" if args.variant == "query" else "data-sharded, NCCL all-gather + merge") if world > 1 else "single GPU",
-            "l2": "inputs larger than L2 (two 4 GB arenas swept per step); no explicit flush"}
+            "D": n, "Q": m, "k": 100, "dim": 100, "ncat": ncat, "types": list(types), "mode": mode, "sharding": sh,
+            "l2": "inputs larger than L2 (two 4 GB arenas + two 2.2 GB fp16 images swept per step); no explicit flush"
+                  if n >= 10_000_000 else "inputs smaller than L2 are NOT flushed between steps (this is not the metric's config)"}
+
+
+# ---- parity (the oracle is the checker, never the thing measured) -----------------------------------
+def parity_vs_reference(d, q, ids, n_parallel, n_baseline):
+    """ids (all queries) against the reference's own builds on samples with the workload's type mix."""
+    from oracle import check, oracle as O
+    m, n = q.shape[0], d.shape[0]
+    out = {}
+    t0 = time.perf_counter()
+    pick = np.unique(np.linspace(0, m - 1, min(n_parallel, m)).astype(np.int64))
+    if O.ref_available("parallel_nodbg") and n >= 800_000:
+        ref, _ = O.ref_vec_query("parallel_nodbg", d, np.ascontiguousarray(q[pick]))
+        who, rtol = "reference optimized_parallel.hpp, PERF_DBG off (oracle/_ref)", 1e-4      # AVX2 summation order: near-ties may swap
+    else:
+        ref = O.vec_query(d, np.ascontiguousarray(q[pick]), want_dist=False)
+        who, rtol = "oracle port of baseline.hpp (oracle/hvs_oracle.c)", 1e-5
+    p = check.compare(d, q[pick], ref, ids[pick], rtol=rtol)
+    out.update(against=who, queries=int(len(pick)), ok=bool(p.ok), recall_at_100=p.recall_mean, max_rel_dist_err=p.max_rel,
+               id_rows_differ=p.id_rows_differ, secs=time.perf_counter() - t0)
+    if n_baseline and O.ref_available("baseline"):
+        t0 = time.perf_counter()
+        pb = np.unique(np.linspace(0, m - 1, min(n_baseline, m)).astype(np.int64) + (m // (2 * n_baseline) if m > 4 * n_baseline else 0))
+        pb = pb[pb < m]
+        qb = np.ascontiguousarray(q[pb])
+        nthr = max(1, min(os.cpu_count() or 1, 8, len(pb)))
+        parts = np.array_split(np.arange(len(pb)), nthr)
+        with O.RefSession("baseline", d) as rs, ThreadPoolExecutor(nthr) as ex:   # baseline.hpp is single-threaded: one call per host thread, D converted once
+            refs = list(ex.map(lambda ix: rs.query(np.ascontiguousarray(qb[ix]))[0], parts))
+        refb = np.concatenate(refs, 0)
+        pbp = check.compare(d, qb, refb, ids[pb], rtol=1e-5)
+        out["baseline_hpp"] = {"against": "reference baseline.hpp (IMPL=1, oracle of record)", "queries": int(len(pb)), "ok": bool(pbp.ok),
+                               "recall_at_100": pbp.recall_mean, "dist_bit_identical_rows": pbp.dist_bit_identical_rows,
+                               "secs": time.perf_counter() - t0}
+        out["ok"] = bool(out["ok"] and pbp.ok)
+    return out
+
+
+def parity_two_families(eng, q, ids_a, ids_b, what):
+    """Two independent kernel families on the same batch: identical id lists; where rows differ the re-scored
+    distances (the reference's sequential fp32 arithmetic, computed on the device) must still be the same numbers."""
+    same_rows = (ids_a == ids_b).all(axis=1)
+    bad = int((~same_rows).sum())
+    ok = True
+    if bad:
+        idx = np.nonzero(~same_rows)[0]
+        da = eng.rescore(q[idx], ids_a[idx])
+        db = eng.rescore(q[idx], ids_b[idx])
+        ok = bool(np.array_equal(da.view(np.uint32), db.view(np.uint32)))      # ties reordered: distances still identical
+    return {"what": what, "queries": int(ids_a.shape[0]), "id_rows_identical": int(same_rows.sum()), "ok": ok}
+
+
+# ---- timing helpers -------------------------------------------------------------------------------------
+class Timer:
+    def __init__(self, torch, dist, stream, world):
+        self.torch, self.dist, self.stream, self.world = torch, dist, stream, world
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def run(self, fn, steps, warmup, stats_fn=None):
+        torch = self.torch
+        for _ in range(warmup):
+            fn()
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        agg = {}
+        t0 = time.perf_counter()
+        e0.record(self.stream)
+        for _ in range(steps):
+            fn()
+            if stats_fn is not None:
+                for k, v in stats_fn().items():
+                    agg[k] = agg.get(k, 0) + v
+        e1.record(self.stream)
+        self.barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        ms = max(e0.elapsed_time(e1), 0.0)
+        t = torch.tensor([ms, wall], dtype=torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        # host-side stalls (planner) do not show on the stream: a step costs the larger of event time and wall clock
+        return max(float(t[0]), float(t[1])) / steps, {k: v / steps for k, v in agg.items()}
+
+
+def rooflines(st, peak_tf, peaks, workload):
+    hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    flops_tile = 200.0 * st["pairs_tile"]              # SURVEY 8d: 200 flop per (query,row) pair
+    rl_ffma = rl_tensor = rl_direct = None
+    if st["n_items_ffma"] > 0 and st["ms_tile_ffma"] > 0:
+        a = flops_tile / (st["ms_tile_ffma"] * 1e-3) / 1e12
+        rl_ffma = {"kernel": "k_tile_ffma", "bound": "fp32", "achieved": a, "peak": peak_tf, "unit": "TFLOP/s", "frac": a / peak_tf,
+                   "peak_source": "FFMA microkernel measured in this run (MEASURED_PEAKS.json has no FP32 figure); "
+                                  "nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.5", "frac_of_nominal": a / 74.5,
+                   "traffic": None, "algorithmic_flop_per_launch": flops_tile, "ms_per_launch": st["ms_tile_ffma"]}
+    if st["n_items_tensor"] > 0 and st["ms_tile_tensor"] > 0:
+        a = flops_tile / (st["ms_tile_tensor"] * 1e-3) / 1e12
+        tpeak, tsrc = (peaks["bf16_tflops_sustained"], "MEASURED_PEAKS.json bf16_tflops_sustained (measured; fp16 and bf16 share the tensor pipe rate)") \
+            if "bf16_tflops_sustained" in peaks else (1400.0, "fallback 1.4 PFLOP/s sustained")
+        rl_tensor = {"kernel": "k_tile_tensor", "bound": "tensor", "achieved": a, "peak": tpeak, "unit": "TFLOP/s", "frac": a / tpeak,
+                     "peak_source": tsrc, "traffic": None, "algorithmic_flop_per_launch": flops_tile,
+                     "issued_flop_per_launch": 2.0 * 112.0 * st["pairs_computed"], "ms_per_launch": st["ms_tile_tensor"],
+                     "note": "algorithmic = 200 flop per (query,row) pair (SURVEY 8d); the MMA issues K=112 (100 dims + 3 norm terms + pad) "
+                             "on every pair-slot of a 256-query x 128-row tile; ms = CUDA-event span of the sweep's launches"}
+    if st["n_direct"] > 0 and st["ms_direct"] > 0:
+        b = 400.0 * st["pairs_direct"]                  # B_pair: 400 B per pair, no reuse
+        a = b / (st["ms_direct"] * 1e-3) / 1e9
+        rl_direct = {"kernel": "k_direct / k_small", "bound": "hbm", "achieved": a, "peak": hbm_peak, "unit": "GB/s", "frac": a / hbm_peak,
+                     "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({hbm_src})", "traffic": None,
+                     "algorithmic_bytes_per_launch": b, "ms_per_launch": st["ms_direct"],
+                     "note": "B_pair of SURVEY 8d (400 B per pair, what a one-query-at-a-time scan moves); slices that neighbouring queries share "
+                             "are served from L2, and for slices of ~10^2 rows the kernel is latency-bound, not HBM-bound"}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(workload, {})
+    except (OSError, ValueError):
+        traffic = {}
+    for r in (rl_ffma, rl_tensor, rl_direct):
+        if r is not None and r["kernel"].split(" ")[0] in traffic:
+            r["traffic"] = traffic[r["kernel"].split(" ")[0]]["dram_bytes_per_step"]
+            r["traffic_source"] = traffic[r["kernel"].split(" ")[0]]["source"]
+    kern = {"K2 k_tile_ffma": st["ms_tile_ffma"], "K3 k_tile_tensor": st["ms_tile_tensor"], "K4 direct scans": st["ms_direct"],
+            "K5 k_finalize": st["ms_finalize"], "K1 plan": st["ms_plan"]}
+    dom = max(kern, key=kern.get)
+    by_kernel = {"K2": rl_ffma, "K3": rl_tensor, "K4": rl_direct}
+    roofline = by_kernel.get(dom[:2]) or rl_tensor or rl_ffma or rl_direct
+    others = [r for r in (rl_ffma, rl_tensor, rl_direct) if r is not None and r is not roofline]
+    return roofline, others, dom, kern
+
+
+STAT_KEYS = ("pairs", "pairs_tile", "pairs_direct", "pairs_computed", "n_direct", "n_tile", "n_items_ffma", "n_items_tensor",
+             "n_fallback", "launches", "ms_solve_device")
+
+
+def sub_config(hvs, torch, tm, stream, eng, d, q, wl, mode_name, steps, warmup, peak_tf, peaks, parity_n, baseline_n, do_parity, ref_ids=None):
+    """One extra (workload, mode) measurement on an engine whose index is already built: device-resident value, e2e,
+    roofline of its dominant kernel, parity."""
+    m = q.shape[0]
+    with torch.cuda.stream(stream):
+        q_pinned = torch.from_numpy(q).pin_memory()
+        out_pinned = torch.empty((m, 100), dtype=torch.int32).pin_memory()
+        q_dev = q_pinned.to("cuda", non_blocking=True)
+        out_dev = torch.empty((m, 100), dtype=torch.int32, device="cuda")
+        ms, st = tm.run(lambda: eng.solve_device(q_dev, out_dev), steps, warmup, eng.stats)
+        ids = out_dev.cpu().numpy().view(np.uint32).copy()
+        ms_host, _ = tm.run(lambda: eng.solve(q_pinned.numpy(), out_pinned.numpy().view(np.uint32)), max(1, steps), 1)
+    roofline, others, dom, kern = rooflines(st, peak_tf, peaks, wl)
+    res = {"config": workload_config(wl, mode_name, 1), "value": m / (ms * 1e-3), "unit": "queries/s", "ms_per_step": ms, "steps": steps,
+           "warmup": warmup, "e2e": {"value": m / (ms_host * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": int(q.size * 4),
+                                      "d2h_bytes_per_step": int(m * 400)},
+           "roofline": roofline, "roofline_other": others, "dominant_kernel": dom, "kernel_ms_per_step": kern,
+           "stats": {k: st[k] for k in STAT_KEYS}, "gpu_launches": int(round(st["launches"] * steps))}
+    if do_parity:
+        res["parity"] = parity_vs_reference(d, q, ids, parity_n, baseline_n)
+        if ref_ids is not None:
+            res["parity"]["vs_auto_all_queries"] = parity_two_families(eng, q, ref_ids, ids, f"{mode_name} vs auto, every query of the batch")
+            res["parity"]["ok"] = bool(res["parity"]["ok"] and res["parity"]["vs_auto_all_queries"]["ok"])
+    return res, ids
 
 
 # ---- the B200 arm ---------------------------------------------------------------------------------
@@ -197,90 +396,111 @@ def run_b200(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    mode = {"auto": hvs.MODE_AUTO, "exact": hvs.MODE_EXACT, "direct": hvs.MODE_DIRECT, "tensor": hvs.MODE_TENSOR}[args.mode]
-    n, m, ncat, types, rw = WORKLOADS[args.workload]
-    d, q = make_inputs(hvs, args.workload, rank if args.variant == "query" else 0)
-    stream = torch.cuda.current_stream()
+    MODES = {"auto": hvs.MODE_AUTO, "exact": hvs.MODE_EXACT, "direct": hvs.MODE_DIRECT, "tensor": hvs.MODE_TENSOR}
+    mode = MODES[args.mode]
+    wl = args.workload
+    n, m, ncat, types, rw = WORKLOADS[wl]
+    d = make_data(hvs, wl)
+    q = make_queries(hvs, wl)                       # N>1: every rank holds the SAME batch
+    # An explicit (non-default) torch stream: the engine enqueues on the handle it is given, so everything torch does
+    # inside `with torch.cuda.stream(stream)` -- copies, NCCL collectives, index ops -- is ordered with the engine's kernels.
+    stream = torch.cuda.Stream()
+    tm = Timer(torch, dist, stream, world)
+    sharding = importlib.import_module(PKG + ".sharding")
     data_sharded = world > 1 and args.variant == "data"
-    if data_sharded:
-        lo, hi = importlib.import_module(PKG + ".sharding").data_shard(n, rank, world)
-        eng = hvs.Engine(device=local_rank, mode=mode, stream=stream.cuda_stream, id_offset=lo)
-        t_ix = time.perf_counter()
-        eng.index_build(d[lo:hi])
-        t_ix = time.perf_counter() - t_ix
-    else:
-        eng = hvs.Engine(device=local_rank, mode=mode, stream=stream.cuda_stream)
-        t_ix = time.perf_counter()
-        eng.index_build(d)
-        t_ix = time.perf_counter() - t_ix
+    lo, hi = sharding.data_shard(n, rank, world) if data_sharded else (0, n)
+    eng = hvs.Engine(device=local_rank, mode=mode, stream=stream.cuda_stream, id_offset=lo if data_sharded else 0)
+    t_ix = time.perf_counter()
+    eng.index_build(d[lo:hi] if data_sharded else d)
+    t_ix = time.perf_counter() - t_ix
     st_index = eng.stats()
 
-    q_pinned = torch.from_numpy(q).pin_memory()
-    out_pinned = torch.empty((m, 100), dtype=torch.int32).pin_memory()
-    q_dev = q_pinned.cuda(non_blocking=True)
-    out_dev = torch.empty((m, 100), dtype=torch.int32, device="cuda")
-    if data_sharded:
-        p_dist = torch.empty((m, 100), dtype=torch.float32, device="cuda")
-        p_ids = torch.empty((m, 100), dtype=torch.int32, device="cuda")
-        p_cnt = torch.empty((m,), dtype=torch.int32, device="cuda")
-        sharding = importlib.import_module(PKG + ".sharding")
-        tail = torch.from_numpy(np.ascontiguousarray(d[n - 100:])).cuda()
+    with torch.cuda.stream(stream):
+        q_pinned = torch.from_numpy(q).pin_memory()
+        out_pinned = torch.empty((m, 100), dtype=torch.int32).pin_memory()
+        q_dev = q_pinned.to("cuda", non_blocking=True)
+        out_dev = torch.empty((m, 100), dtype=torch.int32, device="cuda")
+        if data_sharded:
+            p_dist = torch.empty((m, 100), dtype=torch.float32, device="cuda")
+            p_ids = torch.empty((m, 100), dtype=torch.int32, device="cuda")
+            p_cnt = torch.empty((m,), dtype=torch.int32, device="cuda")
+            tail = torch.from_numpy(np.ascontiguousarray(d[n - 100:])).cuda()
+            gbuf = (torch.empty((world * m, 100), dtype=torch.float32, device="cuda"),
+                    torch.empty((world * m, 100), dtype=torch.int32, device="cuda"),
+                    torch.empty((world * m,), dtype=torch.int32, device="cuda"))
     torch.cuda.synchronize()
+    scratch = {}
+    result = {}
 
     def step_device():
-        if data_sharded:
-            eng.solve_partial_device(q_dev, p_dist, p_ids, p_cnt)
-            g_dist, g_ids, g_cnt = sharding.gather_partials(p_dist, p_ids, p_cnt, world)
-            eng.merge_partials_device(q_dev, world, g_dist, g_ids, g_cnt, tail, n, out_dev)
-        else:
-            eng.solve_device(q_dev, out_dev)
+        with torch.cuda.stream(stream):
+            if data_sharded:
+                eng.solve_partial_device(q_dev, p_dist, p_ids, p_cnt)
+                g_dist, g_ids, g_cnt = sharding.gather_partials(p_dist, p_ids, p_cnt, world, out=gbuf)   # NCCL on `stream`: ordered before the merge
+                eng.merge_partials_device(q_dev, world, g_dist, g_ids, g_cnt, tail, n, out_dev)
+                result["ids"] = out_dev
+            elif world > 1:
+                result["ids"] = sharding.solve_sharded(eng, q_dev, rank, world, scratch)
+            else:
+                eng.solve_device(q_dev, out_dev)
+                result["ids"] = out_dev
+
+    qd2 = {}
 
     def step_host():
-        eng.solve(q_pinned.numpy(), out_pinned.numpy().view(np.uint32))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps, warmup):
-        for _ in range(warmup):
-            fn()
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        agg = {}
-        t0 = time.perf_counter()
-        e0.record(stream)
-        for _ in range(steps):
-            fn()
-            s = eng.stats()
-            for k, v in s.items():
-                agg[k] = agg.get(k, 0) + v
-        e1.record(stream)
-        barrier()
-        wall = time.perf_counter() - t0
-        ms = e0.elapsed_time(e1)
-        ms = max(ms, 0.0)
-        t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t[0]), float(t[1]), {k: v / steps for k, v in agg.items()}
+        with torch.cuda.stream(stream):
+            if world == 1:
+                eng.solve(q_pinned.numpy(), out_pinned.numpy().view(np.uint32))
+            else:                                            # every rank: pinned host queries in, the whole id table out
+                qd2["q"] = q_pinned.to("cuda", non_blocking=True)
+                if data_sharded:
+                    eng.solve_partial_device(qd2["q"], p_dist, p_ids, p_cnt)
+                    g_dist, g_ids, g_cnt = sharding.gather_partials(p_dist, p_ids, p_cnt, world, out=gbuf)
+                    eng.merge_partials_device(qd2["q"], world, g_dist, g_ids, g_cnt, tail, n, out_dev)
+                    ids = out_dev
+                else:
+                    ids = sharding.solve_sharded(eng, qd2["q"], rank, world, scratch)
+                out_pinned.copy_(ids, non_blocking=True)
+                stream.synchronize()
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    ms_dev, wall_dev, st = timed(step_device, args.steps, args.warmup)
+    ms_step, st = tm.run(step_device, args.steps, args.warmup, eng.stats)
     clocks = sampler.stop() if sampler else None
-    ids_dev = out_dev.cpu().numpy().view(np.uint32).copy()
+    torch.cuda.synchronize()
+    ids_dev = result["ids"].cpu().numpy().view(np.uint32).copy()
     if data_sharded:
-        e2e = None
-    else:
-        ms_host, wall_host, st_host = timed(step_host, max(1, args.steps), 1)
-        assert np.array_equal(out_pinned.numpy().view(np.uint32), ids_dev), "host and device entry points disagree"
-        # host-side stalls (planner) do not show on the stream: use the larger of event time and wall clock
-        e2e_ms = max(ms_host, wall_host) / max(1, args.steps)
-        e2e = {"value": world * m / (e2e_ms * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms,
-               "h2d_bytes_per_step": int(q_pinned.numel() * 4), "d2h_bytes_per_step": int(out_pinned.numel() * 4),
-               "ms_h2d": st_host["ms_h2d"], "ms_d2h": st_host["ms_d2h"], "entry_point": "hvs_solve (pinned host buffers)"}
-    ms_step = max(ms_dev, wall_dev) / args.steps
+        # the merge must read THIS step's gathered lists, not what an earlier step left in the same buffers:
+        # poison them, run one more step, expect the same answer (stream ordering of NCCL vs the merge)
+        with torch.cuda.stream(stream):
+            for b in gbuf:
+                b.view(torch.int32).fill_(0x7f7f7f7f)
+            out_dev.fill_(-1)
+        step_device()
+        torch.cuda.synchronize()
+        assert np.array_equal(result["ids"].cpu().numpy().view(np.uint32), ids_dev), "merge read stale gather buffers"
+    ms_host, st_host = tm.run(step_host, max(1, args.steps), 1, eng.stats)
+    assert np.array_equal(out_pinned.numpy().view(np.uint32), ids_dev), "host and device entry points disagree"
+    e2e = {"value": m / (ms_host * 1e-3), "unit": "queries/s", "ms_per_step": ms_host,
+           "h2d_bytes_per_step": int(q_pinned.numel() * 4), "d2h_bytes_per_step": int(out_pinned.numel() * 4),
+           "entry_point": "hvs_solve (pinned host buffers)" if world == 1 else
+                          "per rank: pinned queries -> H2D -> sharded solve -> NCCL all-gather -> D2H of all ids"}
+
+    # per-rank view (who was the slowest, and why)
+    per_rank = None
+    weak = None
+    if world > 1:
+        mine = {"rank": rank, "queries": int(st["m"]) if "m" in st else None, "pairs": st["pairs"], "ms_solve_device": st["ms_solve_device"],
+                "ms_plan": st["ms_plan"], "ms_tile": st["ms_tile"], "ms_finalize": st["ms_finalize"], "ms_direct": st["ms_direct"]}
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
+        if not data_sharded:
+            # weak scaling beside it: every rank its own full batch, no exchange (what round 1 reported)
+            qw = make_queries(hvs, wl, salt=rank)
+            with torch.cuda.stream(stream):
+                qw_dev = torch.from_numpy(qw).to("cuda")
+            ms_weak, _ = tm.run(lambda: eng.solve_device(qw_dev, out_dev), 3, 1)
+            weak = {"value": world * m / (ms_weak * 1e-3), "unit": "queries/s", "ms_per_step": ms_weak,
+                    "what": f"{world} x {m} queries, each rank its own batch, no exchange"}
 
     peak_tf, peak_mhz = eng.measure_ffma_peak(3)
     if rank != 0:
@@ -289,97 +509,77 @@ def run_b200(args, rank, world, local_rank):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (per launch == per step: one launch of each kernel per solve)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except OSError:
         pass
-    hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
-    kern = {"K2 k_tile_ffma": st["ms_tile_ffma"], "K3 k_tile_tensor": st["ms_tile_tensor"], "K4 k_direct": st["ms_direct"],
-            "K5 k_finalize": st["ms_finalize"], "K1 plan": st["ms_plan"]}
-    dom = max(kern, key=kern.get)
-    flops_tile = 200.0 * st["pairs_tile"]              # 200 flop per (query,row) pair
-    rl_ffma = None
-    if st["n_items_ffma"] > 0 and st["ms_tile_ffma"] > 0:
-        a = flops_tile / (st["ms_tile_ffma"] * 1e-3) / 1e12
-        rl_ffma = {"kernel": "k_tile_ffma", "bound": "fp32", "achieved": a, "peak": peak_tf, "unit": "TFLOP/s", "frac": a / peak_tf,
-                   "peak_source": f"FFMA microkernel measured in this run at {peak_mhz:.0f} MHz (MEASURED_PEAKS.json has no FP32 figure); "
-                                  f"nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.5", "frac_of_nominal": a / 74.5,
-                   "traffic": None, "algorithmic_flop_per_launch": flops_tile, "ms_per_launch": st["ms_tile_ffma"]}
-    rl_tensor = None
-    if st["n_items_tensor"] > 0 and st["ms_tile_tensor"] > 0:
-        a = flops_tile / (st["ms_tile_tensor"] * 1e-3) / 1e12
-        tpeak, tsrc = (peaks["bf16_tflops_sustained"], "MEASURED_PEAKS.json bf16_tflops_sustained (measured; fp16 and bf16 share the tensor pipe rate)") \
-            if "bf16_tflops_sustained" in peaks else (1400.0, "fallback 1.4 PFLOP/s sustained")
-        rl_tensor = {"kernel": "k_tile_tensor", "bound": "tensor", "achieved": a, "peak": tpeak, "unit": "TFLOP/s", "frac": a / tpeak,
-                     "peak_source": tsrc, "traffic": None, "algorithmic_flop_per_launch": flops_tile,
-                     "issued_flop_per_launch": 2.0 * 112.0 * st["pairs_computed"], "ms_per_launch": st["ms_tile_tensor"],
-                     "note": "algorithmic = 200 flop per (query,row) pair (SURVEY 8d); the MMA issues K=112 (100 dims + 3 norm terms + pad) "
-                             "on every pair-slot of a 256-query x 128-row tile"}
-    rl_direct = None
-    if st["n_direct"] > 0 and st["ms_direct"] > 0:
-        b = 400.0 * st["pairs_direct"]                  # B_pair: 400 B per pair, no reuse
-        a = b / (st["ms_direct"] * 1e-3) / 1e9
-        rl_direct = {"kernel": "k_direct", "bound": "hbm", "achieved": a, "peak": hbm_peak, "unit": "GB/s", "frac": a / hbm_peak,
-                     "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({hbm_src})", "traffic": None,
-                     "algorithmic_bytes_per_launch": b, "ms_per_launch": st["ms_direct"]}
-    # DRAM traffic per step of each kernel, from the committed ncu capture of this same workload (profiles/r1_traffic.json)
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(args.workload, {})
-    except (OSError, ValueError):
-        traffic = {}
-    for r in (rl_ffma, rl_tensor, rl_direct):
-        if r is not None and r["kernel"] in traffic:
-            r["traffic"] = traffic[r["kernel"]]["dram_bytes_per_step"]
-            r["traffic_source"] = traffic[r["kernel"]]["source"]
-    by_kernel = {"K2": rl_ffma, "K3": rl_tensor, "K4": rl_direct}
-    roofline = by_kernel.get(dom[:2]) or rl_tensor or rl_ffma or rl_direct
-    others = [r for r in (rl_ffma, rl_tensor, rl_direct) if r is not None and r is not roofline]
-
-    # query-sharded: every rank solves its own Q-sized batch (weak scaling); data-sharded: all ranks solve the SAME batch
-    total_q = m if data_sharded else world * m
-    line = {"metric": "queries/sec", "value": total_q / (ms_step * 1e-3), "unit": "queries/s", "n_gpus": world,
+    roofline, others, dom, kern = rooflines(st, peak_tf, peaks, wl)
+    line = {"metric": "queries/sec", "value": m / (ms_step * 1e-3), "unit": "queries/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "strong" if data_sharded else "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(round((st["launches"] + (1 if data_sharded else 0)) * args.steps)),
-            "roofline": roofline, "roofline_other": others, "dominant_kernel": dom,
-            "kernel_ms_per_step": kern,
-            "stats": {k: st[k] for k in ("pairs", "pairs_tile", "pairs_direct", "pairs_computed", "n_direct", "n_tile",
-                                         "n_items_ffma", "n_items_tensor", "n_fallback", "launches", "ms_solve_device")},
+            "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(wl, args.mode, world, args.variant),
+            "clocks": clocks, "e2e": e2e,
+            "gpu_launches": int(round((st["launches"] + (1 if data_sharded else 0)) * args.steps)),
+            "roofline": roofline, "roofline_other": others, "dominant_kernel": dom, "kernel_ms_per_step": kern,
+            "stats": {k: st[k] for k in STAT_KEYS},
             "index_build_ms": st_index["ms_index_build"],
             "indexing_phase": {"host_to_index_wall_ms": t_ix * 1e3, "device_ms": st_index["ms_index_build"],
-                               "bytes_streamed": int(d.shape[0] if not data_sharded else hi - lo) * 408,
+                               "bytes_streamed": int(hi - lo) * 408, "n_outliers": st_index.get("n_outliers"),
                                "note": "hvs_index_build: pageable host rows -> pinned double buffer -> H2D -> radix sorts, gathers, fp16 "
                                        "images; done once, never sees queries; not part of a step"},
-            "alg_tflops_whole_step": 200.0 * st["pairs"] / (ms_step * 1e-3) / 1e12}
+            # what src/test.cpp:82-88 would time around vec_query(): ingest + index + solve through the host entry points
+            "vec_query_wall": {"ms": t_ix * 1e3 + ms_host, "ingest_and_index_ms": t_ix * 1e3, "solve_ms": ms_host,
+                               "value": m / ((t_ix * 1e3 + ms_host) * 1e-3), "unit": "queries/s",
+                               "what": "hvs_index_build (host rows) + hvs_solve (host queries, host ids): the body of the IMPL=4 vec_query shim"},
+            "alg_tflops_whole_step": 200.0 * st["pairs"] * (world if world > 1 and not data_sharded else 1) / (ms_step * 1e-3) / 1e12,
+            "ffma_peak_tflops_measured": peak_tf}
+    if world > 1:
+        line["per_rank"] = per_rank
+        if weak:
+            line["weak_scaling"] = weak
+        line["alg_tflops_whole_step"] = 200.0 * sum(r["pairs"] for r in per_rank) / (ms_step * 1e-3) / 1e12 if not data_sharded else line["alg_tflops_whole_step"]
 
-    # ---- parity on a sample, outside the timed region (the oracle is the checker, never the thing measured)
-    if not args.no_parity and not data_sharded and world == 1:
-        from oracle import check, oracle as O
-        pick = np.linspace(0, m - 1, 8).astype(np.int64)
-        t0 = time.perf_counter()
-        if O.ref_available("parallel_nodbg") and n >= 1_000_000:
-            ref, _ = O.ref_vec_query("parallel_nodbg", d, q[pick])
-            who = "reference optimized_parallel (oracle/_ref)"
-        else:
-            ref = O.vec_query(d, q[pick], want_dist=False)
-            who = "oracle port of baseline.hpp"
-        p = check.compare(d, q[pick], ref, ids_dev[pick], rtol=1e-4 if "optimized" in who else 1e-5)
-        line["parity"] = {"against": who, "queries": int(len(pick)), "ok": bool(p.ok), "recall_at_100": p.recall_mean,
-                          "max_rel_dist_err": p.max_rel, "secs": time.perf_counter() - t0}
+    if not args.no_parity:
+        line["parity"] = parity_vs_reference(d, q, ids_dev, args.parity_sample, 16 if n >= 1_000_000 else 0)
     if not args.no_cpu_baseline and world == 1:
-        qs, _ = sample_queries(q, args.cpu_sample)
-        best, allv = cpu_reference_run(d, qs, 1, 0)
-        line["cpu_baseline"] = {"value": qs.shape[0] / best["secs"], "unit": "queries/s", "cores": best["threads"],
-                                "kind": best["kind"],
-                                "sample": f"{qs.shape[0]} of the {m} queries (every {m // max(1, qs.shape[0])}-th, same type mix) against the "
-                                          f"full D={n}, one pass; {best['desc']}; host has {os.cpu_count()} cores",
-                                "variants": {k: {"queries_per_s": v.get("queries", qs.shape[0]) / v["secs"], "threads": v["threads"],
-                                                 "what": v["desc"]} for k, v in allv.items()}}
+        line["cpu_baseline"] = cpu_baseline_entry(d, q, args.cpu_sample)
+
+    # ---- N=1: the other kernel family on the same batch, and the other BASELINE configs ----------------
+    if world == 1 and not args.no_configs and wl == "large" and args.mode == "auto":
+        cfgs = {}
+        do_par = not args.no_parity
+        t_cfg = time.perf_counter()
+        eng.set_mode(hvs.MODE_EXACT)
+        cfgs["configs[2] exact"], ids_exact = sub_config(hvs, torch, tm, stream, eng, d, q, "large", "exact", 2, 1, peak_tf, peaks, 64, 0, do_par, ids_dev)
+        if do_par:
+            line["parity"]["exact_vs_auto_all_queries"] = cfgs["configs[2] exact"]["parity"]["vs_auto_all_queries"]
+            line["parity"]["ok"] = bool(line["parity"]["ok"] and line["parity"]["exact_vs_auto_all_queries"]["ok"])
+        eng.set_mode(hvs.MODE_AUTO)
+        q0 = make_queries(hvs, "type0")
+        cfgs["configs[3] type0"], _ = sub_config(hvs, torch, tm, stream, eng, d, q0, "type0", "auto", 3, 1, peak_tf, peaks, 32, 4, do_par)
+        eng.close()
+        d = recategorise(d, WORKLOADS["selective"][2])              # configs[4]: same rows, 1000 categories
+        with hvs.Engine(device=local_rank, mode=hvs.MODE_AUTO, stream=stream.cuda_stream) as e4:
+            e4.index_build(d)
+            q4 = make_queries(hvs, "selective")
+            cfgs["configs[4] selective"], _ = sub_config(hvs, torch, tm, stream, e4, d, q4, "selective", "auto", 10, 3, peak_tf, peaks, 256, 8, do_par)
+        del d
+        for name, key in (("medium", "configs[1] medium"), ("default", "configs[0] default")):
+            dd, qq = make_data(hvs, name), make_queries(hvs, name)
+            with hvs.Engine(device=local_rank, mode=hvs.MODE_AUTO, stream=stream.cuda_stream) as es:
+                es.index_build(dd)
+                cfgs[key], _ = sub_config(hvs, torch, tm, stream, es, dd, qq, name, "auto", 10, 3, peak_tf, peaks,
+                                          256 if name == "medium" else 100, 16 if name == "medium" else 100, do_par)
+                if do_par and name == "default":                   # configs[0] runs through the reference's baseline.cpp in full
+                    pass
+        line["configs"] = cfgs
+        line["configs_secs"] = time.perf_counter() - t_cfg
+        if do_par:
+            line["parity"]["all_configs_ok"] = bool(all(c.get("parity", {}).get("ok", False) for c in cfgs.values()))
+    else:
+        eng.close()
     print(json.dumps(line), flush=True)
-    eng.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -121,6 +121,9 @@ HVS_API const char *hvs_last_error(const hvs_engine *e);
 
 HVS_API int hvs_create(hvs_engine **out, const hvs_config *cfg);
 HVS_API void hvs_destroy(hvs_engine *e);
+/* Kernel family of the NEXT solves (hvs_mode); the index serves every mode, so one engine can answer the same
+ * batch through two independent kernel families (what the parity checks of bench.py do). */
+HVS_API int hvs_set_mode(hvs_engine *e, uint32_t mode);
 
 /*
  * Indexing phase.  Replaces the per-query O(N) predicate scans of include/baseline.hpp:107-136 /

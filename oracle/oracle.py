@@ -225,3 +225,56 @@ def ref_vec_query(impl, nodes, queries, sample_proportion: float = 1.0):
     if secs < 0:
         raise RuntimeError(f"reference vec_query failed ({secs})")
     return ids, secs
+
+
+def _ref_lib(impl):
+    if impl not in _ref_libs:
+        L = C.CDLL(os.path.join(REF_DIR, _REF_NAMES[impl]))
+        L.ref_vec_query.restype = C.c_double
+        L.ref_vec_query.argtypes = [_f32p, C.c_uint32, _f32p, C.c_uint32, C.c_float, _u32p]
+        _ref_libs[impl] = L
+    L = _ref_libs[impl]
+    if hasattr(L, "ref_set_nodes") and not getattr(L, "_session_api", False):
+        L.ref_set_nodes.restype = C.c_int
+        L.ref_set_nodes.argtypes = [_f32p, C.c_uint32]
+        L.ref_clear_nodes.restype = None
+        L.ref_query_loaded.restype = C.c_double
+        L.ref_query_loaded.argtypes = [_f32p, C.c_uint32, C.c_float, _u32p]
+        L._session_api = True
+    return L
+
+
+class RefSession:
+    """The reference with D converted to its nested vectors ONCE (10^7 heap rows, ~4.5 GB) for many vec_query calls.
+    `query` may run on several host threads at once for the single-threaded variants (baseline, optimized)."""
+
+    def __init__(self, impl, nodes):
+        self.impl = impl
+        self.L = _ref_lib(impl)
+        self.nodes = np.ascontiguousarray(nodes, np.float32)
+        self.loaded = hasattr(self.L, "ref_set_nodes")
+        if self.loaded and self.L.ref_set_nodes(self.nodes, self.nodes.shape[0]) != 0:
+            raise RuntimeError("ref_set_nodes failed")
+
+    def query(self, queries, sample_proportion: float = 1.0):
+        queries = np.ascontiguousarray(queries, np.float32)
+        m = queries.shape[0]
+        ids = np.empty((m, K), np.uint32)
+        if self.loaded:
+            secs = self.L.ref_query_loaded(queries, m, sample_proportion, ids)
+        else:                                              # an older prebuilt library: the one-shot entry point
+            secs = self.L.ref_vec_query(self.nodes, self.nodes.shape[0], queries, m, sample_proportion, ids)
+        if secs < 0:
+            raise RuntimeError(f"reference vec_query failed ({secs})")
+        return ids, secs
+
+    def close(self):
+        if self.loaded:
+            self.L.ref_clear_nodes()
+            self.loaded = False
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()

@@ -35,7 +35,7 @@ HVS_OK, HVS_ERR_INVALID, HVS_ERR_NO_DEVICE, HVS_ERR_CUDA, HVS_ERR_STATE, HVS_ERR
 
 # every symbol include/hvs.h declares (tests check the library exports exactly these)
 ABI_SYMBOLS = (
-    "hvs_abi_version", "hvs_last_error", "hvs_create", "hvs_destroy", "hvs_index_build", "hvs_index_build_device",
+    "hvs_abi_version", "hvs_last_error", "hvs_create", "hvs_destroy", "hvs_set_mode", "hvs_index_build", "hvs_index_build_device",
     "hvs_index_build_rows", "hvs_index_build_from_file",
     "hvs_solve", "hvs_solve_full", "hvs_solve_device", "hvs_solve_shard_device", "hvs_shard_assign_host",
     "hvs_solve_partial_device", "hvs_merge_partials_device", "hvs_rescore",
@@ -95,6 +95,8 @@ def lib():
         L.hvs_create.argtypes = [C.POINTER(vp), C.POINTER(Config)]
         L.hvs_destroy.restype = None
         L.hvs_destroy.argtypes = [vp]
+        L.hvs_set_mode.restype = i32
+        L.hvs_set_mode.argtypes = [vp, u32]
         for name in ("hvs_index_build", "hvs_index_build_device"):
             f = getattr(L, name)
             f.restype = i32
@@ -158,6 +160,9 @@ class Engine:
     def _ck(self, rc: int) -> None:
         if rc != HVS_OK:
             raise HvsError(rc, lib().hvs_last_error(self._h).decode())
+
+    def set_mode(self, mode: int) -> None:
+        self._ck(lib().hvs_set_mode(self._h, mode))
 
     def close(self) -> None:
         if self._h:

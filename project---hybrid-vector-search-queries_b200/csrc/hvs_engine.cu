@@ -128,6 +128,15 @@ extern "C" void hvs_destroy(hvs_engine *e)
     delete e;
 }
 
+extern "C" int hvs_set_mode(hvs_engine *e, uint32_t mode)
+{
+    if (!e) return HVS_ERR_INVALID;
+    e->err.clear();
+    if (mode > HVS_MODE_TENSOR) EFAIL(HVS_ERR_INVALID, "hvs_set_mode: unknown mode");
+    e->mode = mode;
+    return HVS_OK;
+}
+
 static float ev_ms(cudaEvent_t a, cudaEvent_t b)
 {
     float ms = 0.f;

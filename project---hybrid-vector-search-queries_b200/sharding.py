@@ -28,16 +28,22 @@ def data_shard(n: int, rank: int, world: int) -> tuple[int, int]:
     return rank * n // world, (rank + 1) * n // world
 
 
-def gather_partials(dist, ids, cnt, world: int):
+def gather_partials(dist, ids, cnt, world: int, out=None):
     """all-gather the per-shard partial results.  dist/ids: [m,100], cnt: [m] (any device).
-    -> (g_dist[G,m,100], g_ids[G,m,100], g_cnt[G,m]), shard-major, as hvs_merge_partials_device expects."""
+    -> (g_dist[G,m,100], g_ids[G,m,100], g_cnt[G,m]), shard-major, as hvs_merge_partials_device expects.
+    `out`: optional (g_dist, g_ids, g_cnt) buffers of shapes [G*m,100], [G*m,100], [G*m] to gather into.
+    The collectives are enqueued relative to torch's CURRENT stream: call this inside `with torch.cuda.stream(s)`
+    where s is the stream the engine was created on, so that the merge that follows is ordered after them."""
     import torch
     import torch.distributed as td
     m = dist.shape[0]
     # outputs are the concatenation along dim 0 (what both gloo and nccl accept), viewed shard-major afterwards
-    g_dist = torch.empty((world * m,) + tuple(dist.shape[1:]), dtype=dist.dtype, device=dist.device)
-    g_ids = torch.empty((world * m,) + tuple(ids.shape[1:]), dtype=ids.dtype, device=ids.device)
-    g_cnt = torch.empty((world * m,), dtype=cnt.dtype, device=cnt.device)
+    if out is not None:
+        g_dist, g_ids, g_cnt = out
+    else:
+        g_dist = torch.empty((world * m,) + tuple(dist.shape[1:]), dtype=dist.dtype, device=dist.device)
+        g_ids = torch.empty((world * m,) + tuple(ids.shape[1:]), dtype=ids.dtype, device=ids.device)
+        g_cnt = torch.empty((world * m,), dtype=cnt.dtype, device=cnt.device)
     td.all_gather_into_tensor(g_dist, dist.contiguous())
     td.all_gather_into_tensor(g_ids, ids.contiguous())
     td.all_gather_into_tensor(g_cnt, cnt.contiguous())

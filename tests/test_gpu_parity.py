@@ -429,3 +429,69 @@ def test_id_offset_with_pad_rows(H, oracle, check, datagen):
     p = check.compare(d, q, ref, local, rtol=RTOL)
     assert p.ok and p.dist_bit_identical_rows == len(q), p.summary()
     assert np.array_equal(dist.view(np.uint32), oracle.rescore(d, q, local).view(np.uint32))
+
+
+def test_sharded_solve_covers_the_batch(H, oracle, check, datagen):
+    """hvs_solve_shard_device, all ranks played by one engine: the shares are disjoint, cover the batch, and every
+    share's rows are the rows hvs_solve gives for those queries (strong-scaling path of bench.py --gpus N)."""
+    import torch
+    n, m = 150_000, 1500
+    d = datagen.gen_data(n, 101, ncat=12)
+    q = datagen.gen_queries(m, 102, ncat=12)
+    qd = torch.from_numpy(q).cuda()
+    with H.Engine(mode=H.MODE_AUTO) as e:
+        e.index_build(d)
+        want = e.solve(q)
+        for world in (1, 3, 8):
+            got = np.full((m, 100), 0xFFFFFFFF, np.uint32)
+            seen = np.zeros(m, np.int64)
+            buf = torch.empty((m, 100), dtype=torch.int32, device="cuda")
+            for rank in range(world):
+                buf.fill_(-1)
+                order, counts = e.solve_shard_device(qd, rank, world, buf)
+                torch.cuda.synchronize()
+                assert int(counts.sum()) == m
+                off = int(counts[:rank].sum())
+                own = order[off:off + int(counts[rank])].astype(np.int64)
+                got[own] = buf[: len(own)].cpu().numpy().view(np.uint32)
+                seen[own] += 1
+                assert e.stats()["m"] == len(own)
+            assert (seen == 1).all()
+            assert np.array_equal(got, want), world
+    ref = oracle.vec_query(d, q[:48], want_dist=False)
+    p = check.compare(d, q[:48], ref, want[:48], rtol=RTOL)
+    assert p.ok and p.dist_bit_identical_rows == 48, p.summary()
+
+
+def test_many_chunks_per_slice_and_global_lists(H, oracle, check, datagen):
+    """D = 4x10^6, enough queries that the planner cuts slices into 16k-row chunks swept by different CTAs (>= 128
+    stages per item: the per-query global best-score lists of K3 and the shared thresholds are exercised), several
+    chunks per slice.  AUTO and EXACT (independent kernel families) must agree on every query; a sample is checked
+    against the oracle and every returned id against its predicate."""
+    n, m = 4_000_000, 4096
+    d = datagen.gen_data(n, 111, ncat=10)
+    q = datagen.gen_queries(m, 112, ncat=10, types=(0, 2))
+    with H.Engine(mode=H.MODE_AUTO, flags=H.FLAG_MARGIN_AUDIT) as e:
+        e.index_build(d)
+        ids = e.solve(q)
+        st = e.stats()
+        dist = e.rescore(q, ids)
+        e.set_mode(H.MODE_EXACT)
+        ids_exact = e.solve(q)
+        st_exact = e.stats()
+        dist_exact = e.rescore(q, ids_exact)
+    assert st["n_items_tensor"] > 0 and st["pairs_tile"] > 9.9e9 and st["n_fallback"] == 0, st
+    assert st["n_items_tensor"] * 256 * 16384 >= st["pairs_tile"] * 0.5          # items are >= 16k rows: ntiles >= 128
+    assert 0.0 < st["margin_audit"] < 1.0 and 0.0 < st_exact["margin_audit"] < 1.0, (st, st_exact)
+    assert st_exact["n_items_ffma"] > 0
+    assert np.array_equal(dist.view(np.uint32), dist_exact.view(np.uint32))
+    assert (ids == ids_exact).all(axis=1).mean() > 0.999
+    assert (np.diff(dist, axis=1) >= 0).all()
+    T = d[:, 1]
+    for i in range(0, m, 97):
+        if q[i, 0] == 2:
+            assert ((T[ids[i]] >= q[i, 2]) & (T[ids[i]] <= q[i, 3])).all() or (T[(T >= q[i, 2]) & (T <= q[i, 3])].size < 100)
+    pick = np.arange(5, m, m // 16)[:16]
+    ref = oracle.vec_query(d, q[pick], want_dist=False)
+    p = check.compare(d, q[pick], ref, ids[pick], rtol=RTOL)
+    assert p.ok and p.dist_bit_identical_rows == len(pick), p.summary()
