@@ -46,6 +46,11 @@ inline void flatten(const std::vector<std::vector<float>> &rows, size_t width, s
     for (auto &t : th) t.join();
 }
 
+// Optional side channel for drivers that also want the `.dist` table (src/test.cpp:97-110 rebuilds it from 100 copied
+// rows per query; SaveKNNFull, include/io.h:50-78): point this at a vector before calling vec_query and it receives
+// queries.size() x 100 distances, computed on the device by hvs_solve_full in the same call -- one index build.
+inline std::vector<float> *want_dist = nullptr;
+
 }  // namespace hvs_shim
 
 inline void vec_query(std::vector<std::vector<float>> &nodes, std::vector<std::vector<float>> &queries,
@@ -71,7 +76,10 @@ inline void vec_query(std::vector<std::vector<float>> &nodes, std::vector<std::v
     if (hvs_index_build_rows(e, rows.data(), (uint32_t)nodes.size(), sample_proportion) != HVS_OK) hvs_shim::die(e, "hvs_index_build_rows");
     const uint32_t m = (uint32_t)queries.size();
     std::vector<uint32_t> ids((size_t)m * HVS_K);
-    if (hvs_solve(e, q.data(), m, ids.data()) != HVS_OK) hvs_shim::die(e, "hvs_solve");
+    if (hvs_shim::want_dist) {
+        hvs_shim::want_dist->resize((size_t)m * HVS_K);
+        if (hvs_solve_full(e, q.data(), m, ids.data(), hvs_shim::want_dist->data()) != HVS_OK) hvs_shim::die(e, "hvs_solve_full");
+    } else if (hvs_solve(e, q.data(), m, ids.data()) != HVS_OK) hvs_shim::die(e, "hvs_solve");
     knn_results.reserve(knn_results.size() + m);
     for (uint32_t i = 0; i < m; ++i)
         knn_results.emplace_back(ids.begin() + (size_t)i * HVS_K, ids.begin() + (size_t)(i + 1) * HVS_K);

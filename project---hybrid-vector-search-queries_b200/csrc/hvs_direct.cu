@@ -74,6 +74,129 @@ k_direct(const float *__restrict__ queries, const QSlice *__restrict__ slices, c
     finish_query(S.top, S.q, A, len, tail, n_total, id_offset, q, partial != 0, out_ids, out_dist, out_count, tid, DT);
 }
 
+// ---- K4s: tiny slices, one WARP per query ---------------------------------------------------------------------------
+// Selective predicates (a category AND a narrow T range: SURVEY 2.2 "K4 small-slice", BASELINE configs[4]) leave 10^1..10^3
+// rows per query.  A CTA per query, a 51 KB TMA stage and block-wide sorts are all fixed cost at that size, so these
+// queries get a warp each (8 per CTA, no block-level synchronisation at all): lane = row, rows read straight from
+// global memory (consecutive rows: the 32 lanes cover one contiguous 12.8 KB run), distances in the reference's
+// arithmetic (ref_dist_row), candidates appended to a 256-entry list in shared memory by ballot, the list cut to the
+// best 100 by a warp bitonic sort whenever it fills, the pad rule (include/baseline.hpp:138-147) applied from the
+// resident tail buffer, one final warp sort, 100 ids written.  The kernel decides per query, on the device, whether the
+// slice is small enough (len <= small_max) -- so it can be launched right behind the slice search, for ALL queries,
+// before the host has seen a single slice; the host planner leaves those queries alone.
+// Roof: latency (a dependent chain of 100 fp32 adds per row, two or three round trips to L2/HBM per query), not
+// bandwidth: ~20 KB of rows per query.
+constexpr int SW = 8;        // warps (queries) per CTA
+constexpr int SCAP = 256;    // candidate list entries per warp
+
+struct SmallSmem {
+    uint64_t cand[SW][SCAP];
+    alignas(16) float q[SW][DIM];
+};
+
+__global__ void __launch_bounds__(SW * 32)
+k_small(const float *__restrict__ queries, const QSlice *__restrict__ slices, const uint32_t *__restrict__ q_list, uint32_t nq,
+        uint32_t small_max, Arena a0, Arena a1, const float *__restrict__ tail, uint32_t n_total, uint32_t id_offset,
+        int partial, uint32_t *__restrict__ out_ids, float *__restrict__ out_dist, uint32_t *__restrict__ out_count)
+{
+    __shared__ SmallSmem S;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t qi = blockIdx.x * SW + w;
+    if (qi >= nq) return;
+    const uint32_t q = q_list ? q_list[qi] : qi;
+    const QSlice sl = slices[q];
+    const uint32_t len = sl.end - sl.begin;
+    if (len > small_max) return;                                       // the planner routes this query (tile sweep or CTA scan)
+    const Arena A = sl.arena == ARENA_T ? a0 : a1;
+    uint64_t *cand = S.cand[w];
+    float *qv = S.q[w];
+    if (lane < DIM / 4)
+        reinterpret_cast<float4 *>(qv)[lane] = reinterpret_cast<const float4 *>(queries + (size_t)q * QROW + 4)[lane];
+    __syncwarp();
+    const float INF = __int_as_float(0x7f800000);
+    uint32_t cnt = 0;                                                  // warp-uniform
+    float thr = INF;
+    for (uint32_t base = 0; base < len; base += 32) {
+        const uint32_t row = sl.begin + base + lane;
+        const bool valid = base + lane < len;
+        // The whole row first -- 25 independent 16-byte loads in flight, ONE round trip to L2/HBM per 32 rows -- then the
+        // reference's sequential sum.  Lanes past the end re-read the slice's last row (no divergence), and the warp
+        // barrier keeps the compiler from sinking the loads into the dependent add chain (it interleaves them otherwise,
+        // three in flight at a time).
+        float d;
+        {
+            const uint32_t rr = valid ? row : sl.end - 1u;
+            const float4 *x4 = reinterpret_cast<const float4 *>(A.x + (size_t)rr * DIM);
+            const float4 *q4 = reinterpret_cast<const float4 *>(qv);
+            float4 xr[DIM / 4];
+#pragma unroll
+            for (int i = 0; i < DIM / 4; ++i) xr[i] = __ldg(x4 + i);
+            __syncwarp();
+            float acc = 0.f;
+#pragma unroll
+            for (int i = 0; i < DIM / 4; ++i) acc = ref_accum4(acc, xr[i], q4[i]);
+            d = valid ? acc : INF;
+        }
+        const bool pass = valid && d < thr;
+        const uint32_t mask = __ballot_sync(0xffffffffu, pass);
+        if (pass) cand[cnt + __popc(mask & ((1u << lane) - 1u))] = pack_key(d, row);
+        cnt += __popc(mask);
+        if (cnt > (uint32_t)(SCAP - 32)) {                             // keep the best K, tighten the threshold
+            for (uint32_t i = cnt + lane; i < (uint32_t)SCAP; i += 32) cand[i] = KEY_INF;
+            __syncwarp();
+            warp_bitonic_sort(cand, SCAP, lane);
+            cnt = K;
+            thr = __uint_as_float((uint32_t)(cand[K - 1] >> 32));
+        }
+    }
+    __syncwarp();
+    if (cnt > (uint32_t)K) {
+        const int n2 = next_pow2((int)cnt);
+        for (uint32_t i = cnt + lane; i < (uint32_t)n2; i += 32) cand[i] = KEY_INF;
+        __syncwarp();
+        warp_bitonic_sort(cand, n2, lane);
+        cnt = K;
+    }
+    // (dist, arena position) -> (dist, id): the output order is by (dist, id) like finish_query's
+    for (uint32_t i = lane; i < cnt; i += 32) {
+        const uint64_t k = cand[i];
+        cand[i] = (k & 0xffffffff00000000ull) | A.ids[(uint32_t)k];
+    }
+    if (!partial && len < (uint32_t)K) {                               // include/baseline.hpp:138-147
+        const uint32_t npad = (uint32_t)K - len;                       // cnt == len here: nothing was ever cut
+        for (uint32_t s = lane; s < npad; s += 32) {
+            const float d = ref_dist_row(tail + (size_t)s * DIM, qv);
+            cand[cnt + s] = pack_key(d, n_total - 1u - s + id_offset);
+        }
+        cnt += npad;
+    }
+    for (uint32_t i = cnt + lane; i < 128u; i += 32) cand[i] = KEY_INF;
+    __syncwarp();
+    warp_bitonic_sort(cand, 128, lane);
+    if (!partial) {
+        for (int i = lane; i < K; i += 32) out_ids[(size_t)q * K + i] = (uint32_t)cand[i];
+    } else {
+        for (int i = lane; i < K; i += 32) {
+            const uint64_t k = cand[i];
+            const bool ok = (uint32_t)i < cnt;
+            out_ids[(size_t)q * K + i] = ok ? (uint32_t)k : 0xffffffffu;
+            out_dist[(size_t)q * K + i] = ok ? __uint_as_float((uint32_t)(k >> 32)) : INF;
+        }
+        if (lane == 0) out_count[q] = len;
+    }
+}
+
+cudaError_t launch_small(hvs_engine *e, const float *queries_dev, const QSlice *slices_dev, const uint32_t *q_list_dev,
+                         uint32_t nq, uint32_t small_max, bool partial, uint32_t *out_ids, float *out_dist, uint32_t *out_count)
+{
+    if (!nq) return cudaSuccess;
+    const Index &ix = e->index;
+    k_small<<<(nq + SW - 1) / SW, SW * 32, 0, e->stream>>>(queries_dev, slices_dev, q_list_dev, nq, small_max, ix.arena(0), ix.arena(1),
+                                                           ix.tail.as<float>(), ix.n_total, ix.id_offset, partial ? 1 : 0, out_ids,
+                                                           out_dist, out_count);
+    return cudaGetLastError();
+}
+
 cudaError_t direct_init_attributes()     // per device; called by hvs_create with the engine's device current
 {
     return cudaFuncSetAttribute(k_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DirectSmem));

@@ -169,7 +169,27 @@ extern "C" int hvs_index_build_device(hvs_engine *e, const float *rows_dev, uint
 // Everything after the slices are known on both sides (d_sl on the device, h_sl on the host): plan, sweeps, finalize.
 // e->ev[2] must have been recorded on the stream before the slice search.
 static int solve_core(hvs_engine *e, const float *q_dev, uint32_t m, const QSlice *d_sl, const QSlice *h_sl, bool partial,
-                      uint32_t *out_ids, float *out_dist, uint32_t *out_count);
+                      uint32_t *out_ids, float *out_dist, uint32_t *out_count, bool small_launched);
+
+// K4s (tiny slices, a warp per query) decides on the device which queries are its own, so it is launched right behind
+// the slice search, before the host has seen a slice.  HVS_SMALL=0 switches it off (everything small takes the CTA scan).
+static uint32_t small_max()
+{
+    static const uint32_t v = [] { const char *s = getenv("HVS_SMALL"); return (s && s[0] == '0') ? 0u : SMALL_MAX; }();
+    return v;
+}
+static cudaError_t run_small(hvs_engine *e, const float *q_dev, uint32_t m, const QSlice *d_sl, bool partial, uint32_t *out_ids,
+                             float *out_dist, uint32_t *out_count)
+{
+    cudaEventRecord(e->ev[5], e->stream);
+    cudaError_t c = cudaSuccess;
+    if (small_max()) {
+        c = launch_small(e, q_dev, d_sl, nullptr, m, small_max(), partial, out_ids, out_dist, out_count);
+        e->stats.launches++;
+    }
+    cudaEventRecord(e->ev[6], e->stream);
+    return c;
+}
 
 static void reset_solve_stats(hvs_engine *e, uint32_t m)
 {
@@ -193,16 +213,18 @@ static int solve_impl(hvs_engine *e, const float *q_dev, uint32_t m, bool partia
     cudaEventRecord(e->ev[2], s);
     ECUDA(launch_plan_search(e, q_dev, m, d_sl));
     e->stats.launches++;
+    ECUDA(run_small(e, q_dev, m, d_sl, partial, out_ids, out_dist, out_count));   // runs while the slices travel to the host and are planned
     ECUDA(cudaMemcpyAsync(e->h_slices.p, d_sl, (size_t)m * sizeof(QSlice), cudaMemcpyDeviceToHost, s));
     ECUDA(cudaStreamSynchronize(s));
-    return solve_core(e, q_dev, m, d_sl, e->h_slices.as<QSlice>(), partial, out_ids, out_dist, out_count);
+    return solve_core(e, q_dev, m, d_sl, e->h_slices.as<QSlice>(), partial, out_ids, out_dist, out_count, true);
 }
 
 static int solve_core(hvs_engine *e, const float *q_dev, uint32_t m, const QSlice *d_sl, const QSlice *h_sl, bool partial,
-                      uint32_t *out_ids, float *out_dist, uint32_t *out_count)
+                      uint32_t *out_ids, float *out_dist, uint32_t *out_count, bool small_launched)
 {
     hvs_stats &st = e->stats;
     cudaStream_t s = e->stream;
+    if (!small_launched) ECUDA(run_small(e, q_dev, m, d_sl, partial, out_ids, out_dist, out_count));
     if (e->flags & HVS_FLAG_MARGIN_AUDIT) {
         ECUDA(e->d_audit.ensure(4));
         ECUDA(cudaMemsetAsync(e->d_audit.p, 0, 4, s));
@@ -212,6 +234,7 @@ static int solve_core(hvs_engine *e, const float *q_dev, uint32_t m, const QSlic
     pp.mode = e->mode;
     pp.tensor_available = e->index.xb[0].p != nullptr && e->index.xb[1].p != nullptr;
     pp.approx_ok = e->index.approx_ok;
+    pp.small_max = small_max();
     static const long long min_pairs_env = [] { const char *v = getenv("HVS_MIN_TILE_PAIRS"); return v ? atoll(v) : -1ll; }();
     if (min_pairs_env >= 0) pp.min_tile_pairs = (uint64_t)min_pairs_env;   // tests set 0: tile kernels run on tiny inputs too
     Plan &P = e->plan;
@@ -219,7 +242,7 @@ static int solve_core(hvs_engine *e, const float *q_dev, uint32_t m, const QSlic
     st.pairs = P.pairs;
     st.pairs_tile = P.pairs_tile;
     st.pairs_direct = P.pairs - P.pairs_tile;
-    st.n_direct = (uint32_t)P.direct_q.size();
+    st.n_direct = (uint32_t)P.direct_q.size() + P.n_small;
 
     // one pinned staging buffer for all uploads of this solve; every upload gets its own region
     const size_t n_groups = P.group_end.size();
@@ -337,8 +360,9 @@ static int solve_core(hvs_engine *e, const float *q_dev, uint32_t m, const QSlic
     if (e->flags & HVS_FLAG_MARGIN_AUDIT) ECUDA(cudaMemcpyAsync(&st.margin_audit, e->d_audit.p, 4, cudaMemcpyDeviceToHost, s));
     ECUDA(cudaStreamSynchronize(s));
     ECUDA(cudaGetLastError());
-    st.ms_plan = ev_ms(e->ev[2], e->ev[3]);          // slice search + classification; group planning overlaps the sweeps
-    st.ms_direct = ev_ms(e->ev[3], e->ev[4]);
+    const float ms_small = ev_ms(e->ev[5], e->ev[6]);
+    st.ms_plan = std::max(0.f, ev_ms(e->ev[2], e->ev[3]) - ms_small);   // slice search + classification (K4s runs under it); group planning overlaps the sweeps
+    st.ms_direct = ev_ms(e->ev[3], e->ev[4]) + ms_small;
     if (any_items) {
         // the groups' launches overlap (two lanes): the tile phase is the span from the first start to the last end
         float tile = 0.f;
@@ -451,7 +475,7 @@ extern "C" int hvs_solve_shard_device(hvs_engine *e, const float *queries_dev, u
                                     e->d_shard_sl.as<QSlice>()));
         e->stats.launches++;
         rc = solve_core(e, e->d_shard_q.as<float>(), m_own, e->d_shard_sl.as<QSlice>(), e->h_shard_sl.data(), false, out_ids_dev,
-                        nullptr, nullptr);
+                        nullptr, nullptr, false);
     }
     e->stats.ms_solve_wall = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return rc;

@@ -89,6 +89,8 @@ constexpr int QT_TENSOR = 256;   // queries per tensor tile item (K3): two M=128
 constexpr int KOUT = 256;        // candidates an item hands to finalize per query (<= this many)
 constexpr int TENSOR_POOL = 512; // K3: survivor pool entries per (CTA, query) in global memory
 constexpr int TENSOR_GBEST = 128;
+constexpr uint32_t SMALL_MAX = 255;  // K4s: slices of at most this many rows get a warp each (8 rounds of 32 rows; must stay below PlanParams::min_tile_len:
+                                     // never tile queries).  Longer sparse slices take the CTA-per-query scan, which has the lower latency per query.
 constexpr int OUTLIER_MAX = 256;  // K0: most rows that may be set aside as norm outliers // K3: per-query global list of the best scores seen by any CTA
 
 struct TileItem {              // one CTA-sized unit of work: <= 128 queries sweep arena rows [row_begin,row_end)
@@ -112,6 +114,8 @@ struct Plan {
     uint64_t pairs = 0, pairs_computed = 0, pairs_tile = 0;
     uint32_t n_lists = 0;
     uint32_t n_ffma = 0, n_tensor = 0;
+    uint32_t n_small = 0;                 // queries left to K4s (not in direct_q)
+    uint64_t pairs_small = 0;
     // scratch kept between solves (fresh multi-megabyte vectors cost more in page faults than the planning)
     struct Local { std::vector<TileItem> items; std::vector<uint32_t> item_q, cstart, cur, fill; uint64_t pairs_computed = 0; };
     std::vector<Local> locals;
@@ -140,8 +144,8 @@ struct Plan {
     void reset()
     {
         direct_q.clear(); items.clear(); item_q.clear(); tile_q.clear(); q_list_off.clear(); q_lists.clear();
-        pairs = pairs_computed = pairs_tile = 0;
-        n_lists = n_ffma = n_tensor = 0;
+        pairs = pairs_computed = pairs_tile = pairs_small = 0;
+        n_lists = n_ffma = n_tensor = n_small = 0;
         tasks.clear(); group_end.clear(); incid = 0; R = 0;
     }
 };
@@ -150,6 +154,7 @@ struct PlanParams {
     uint32_t mode = HVS_MODE_AUTO;
     uint32_t chunk_rows = 1u << 17;       // max rows an item sweeps
     uint32_t min_tile_len = 1024;         // shorter slices always take the direct scan
+    uint32_t small_max = 0;               // slices of at most this many rows were already solved by K4s (launch_small): neither tile nor direct_q
     double direct_cost_ratio = 12.0;      // FFMA tile pair-slot vs direct pair throughput ratio
     double tensor_min_depth = 0.75;       // tensor items: average queries per row needed (the sweep is bandwidth-, not slot-priced)
     uint64_t min_tile_pairs = 4000000;    // below this many (query,row) pairs a tile sweep's fixed cost (~0.5 ms: persistent launch, operand
@@ -209,6 +214,9 @@ cudaError_t launch_gather_queries(hvs_engine *e, const float *queries_dev, const
 cudaError_t launch_direct(hvs_engine *e, const float *queries_dev, const QSlice *slices_dev,
                           const uint32_t *q_list_dev, uint32_t nq, bool partial,
                           uint32_t *out_ids, float *out_dist, uint32_t *out_count);
+// K4s: every query of q_list (or 0..nq-1) whose slice has at most small_max rows, one warp each; longer ones are skipped.
+cudaError_t launch_small(hvs_engine *e, const float *queries_dev, const QSlice *slices_dev, const uint32_t *q_list_dev,
+                         uint32_t nq, uint32_t small_max, bool partial, uint32_t *out_ids, float *out_dist, uint32_t *out_count);
 cudaError_t launch_tile_ffma(hvs_engine *e, const float *queries_dev, const QSlice *slices_dev,
                              const TileItem *items_dev, uint32_t item_begin, uint32_t n_items,
                              const uint32_t *item_q_dev, uint64_t *cand_dev, uint32_t *cand_cnt_dev,

@@ -203,7 +203,12 @@ void plan_begin(const QSlice *sl, uint32_t m, const PlanParams &pp, Plan &P)
     }
     lap("depth");
     for (uint32_t i = 0; i < m; ++i)
-        if (!is_tile[i]) { P.direct_q.push_back(i); P.pairs_computed += sl[i].end - sl[i].begin; }
+        if (!is_tile[i]) {
+            const uint32_t len = sl[i].end - sl[i].begin;
+            P.pairs_computed += len;
+            if (len <= pp.small_max && pp.small_max) { ++P.n_small; P.pairs_small += std::max(len, (uint32_t)K); }   // K4s has it
+            else P.direct_q.push_back(i);
+        }
     // direct queries: neighbours in an arena share L2 lines.  A counting sort on (arena, begin >> 12) is all the
     // locality the scan needs and costs O(m) (a comparator sort of 4x10^4 slices took 3 ms of a 4 ms solve).
     if (P.direct_q.size() > 1) {

@@ -64,7 +64,8 @@ constexpr int NTHR = 352;              // warp 0 TMA, warp 1 MMA issuer of query
 constexpr int POOL = TENSOR_POOL;     // survivor pool entries per query (global memory)
 constexpr uint32_t FULL = 0xffffffffu;
 constexpr int GB = TENSOR_GBEST;      // per-query global list of best scores over all finished chunks
-constexpr int SPARSE_LANES = 6;       // compaction: up to this many participating lanes are handled one query at a time by the whole warp
+constexpr int SPARSE_LANES = 6;
+constexpr int SPARSE_SEL = 8;         // merge_global: up to this many lanes whose global list needs a new K-th best are handled one query at a time       // compaction: up to this many participating lanes are handled one query at a time by the whole warp
 
 static_assert(QT_TENSOR == 256, "two M=128 halves");
 static_assert(POOL == 512 && KOUT <= POOL - 32, "pool must take 32 more survivors after a compaction");
@@ -144,9 +145,13 @@ struct QState {
 // One call serves up to 32 queries; no sorting, no shuffles, a handful of coalesced passes over the pools.
 __device__ __noinline__ uint2 compact_warp(uint32_t cnt, float thr, float margin, uint32_t qid, bool valid,
                                            uint64_t *__restrict__ pool_warp, uint32_t *__restrict__ gthr,
-                                           uint32_t *__restrict__ flags, uint32_t keep_cap, int lane)
+                                           uint32_t *__restrict__ flags, uint32_t keep_cap, uint32_t part_min, int lane)
 {
-    const bool part = valid && cnt >= (uint32_t)K;                    // lanes that take part
+    // lanes that take part: those whose pool is at least part_min full, and those that have no threshold yet.  A lane
+    // with a threshold and a half-empty pool gains little from a new cut, and leaving it out is what keeps most
+    // compactions on the cheap one-query-at-a-time path below (a warp whose queries begin at different rows --
+    // type-1/3 items -- would otherwise stream all 32 pools every time ONE of them fills).
+    const bool part = valid && cnt >= (uint32_t)K && (cnt >= part_min || thr == __int_as_float(0x7f800000));
     const uint32_t maxc = __reduce_max_sync(FULL, part ? cnt : 0u);
     if (maxc == 0) return make_uint2(cnt, __float_as_uint(thr));
     // Few lanes take part (queries whose slices start at different rows warm up one after the other: type-1/3 items,
@@ -294,7 +299,7 @@ __device__ __noinline__ uint2 compact_warp(uint32_t cnt, float thr, float margin
 __device__ __noinline__ float merge_global(uint32_t cnt, float thr, float margin, uint32_t qid, bool valid,
                                            const uint64_t *__restrict__ pool_warp, uint32_t *__restrict__ gbest,
                                            uint32_t *__restrict__ gcnt, uint32_t *__restrict__ gcut,
-                                           uint32_t *__restrict__ glock, uint32_t *__restrict__ gthr, int lane)
+                                           uint32_t *__restrict__ glock, uint32_t *__restrict__ gthr, bool sparse_ok, int lane)
 {
     const uint32_t *sc = reinterpret_cast<const uint32_t *>(pool_warp) + 2 * lane + 1;   // score word of pool entry i: sc[64 i]
     bool want = valid && cnt > 0;
@@ -341,23 +346,89 @@ __device__ __noinline__ float merge_global(uint32_t cnt, float thr, float margin
         for (int j = 0; j < 32; ++j) nbeat += (part && i0 + j < cnt && k[j] < cut_old) ? 1u : 0u;
     }
     const bool need_sel = part && (gn + nbeat > (uint32_t)GB || (cut_old == 0xffffffffu && gn + nbeat >= (uint32_t)K));
-    if (!__any_sync(FULL, need_sel)) {
-        uint32_t w = gn;
-        for (uint32_t i0 = 0; i0 < maxc; i0 += 32) {
-            uint32_t k[32];
+    const uint32_t selmask = __ballot_sync(FULL, need_sel);
+    const bool sparse_sel = sparse_ok && selmask != 0u && __popc(selmask) <= SPARSE_SEL && maxc <= 256u;
+    if (selmask == 0u || sparse_sel) {
+        // cheap case for the lanes whose list still has room: append the survivors that beat the bound
+        const bool app = part && !need_sel;
+        if (__any_sync(FULL, app)) {
+            uint32_t w = gn;
+            for (uint32_t i0 = 0; i0 < maxc; i0 += 32) {
+                uint32_t k[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) k[j] = __ldcg(sc + (size_t)64 * (i0 + j));
+                for (int j = 0; j < 32; ++j) k[j] = __ldcg(sc + (size_t)64 * (i0 + j));
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-                if (part && i0 + j < cnt && k[j] < cut_old) { G[w] = k[j]; ++w; }
+                for (int j = 0; j < 32; ++j)
+                    if (app && i0 + j < cnt && k[j] < cut_old) { G[w] = k[j]; ++w; }
+            }
+            if (app) {
+                gcnt[qid] = w;
+                __threadfence();
+                atomicExch(&glock[qid], 0u);
+            }
+            __syncwarp();
         }
-        if (part) {
-            gcnt[qid] = w;
+        // Few lanes need a new K-th best (their list would overflow): the WARP takes one such query at a time -- list
+        // (<= 128 scores) and pool (<= 256) go to registers in one round trip, the rank is bracketed with warp-wide
+        // counts, the scores at or below the new bound are written back.  The lane-parallel passes further down cost
+        // the same for one lane as for 32 (every pass is a chain of L2 round trips over all 32 pools).
+        float my_thr = thr;
+        for (uint32_t mm = sparse_sel ? selmask : 0u; mm; mm &= mm - 1u) {
+            const int src = __ffs((int)mm) - 1;
+            const uint32_t c = __shfl_sync(FULL, cnt, src), g_n = __shfl_sync(FULL, gn, src), q_src = __shfl_sync(FULL, qid, src);
+            const float margin_src = __shfl_sync(FULL, margin, src), thr_src = __shfl_sync(FULL, thr, src);
+            uint32_t *Gs = gbest + (size_t)q_src * GB;
+            const uint32_t *scs = reinterpret_cast<const uint32_t *>(pool_warp) + 2 * src + 1;
+            uint32_t e[12];                                                  // 4 list scores + 8 pool scores per lane; 0xffffffff = none
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const uint32_t i = (uint32_t)lane + 32u * j; e[j] = i < g_n ? __ldcg(Gs + i) : 0xffffffffu; }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const uint32_t i = (uint32_t)lane + 32u * j; e[4 + j] = i < c ? __ldcg(scs + (size_t)64 * i) : 0xffffffffu; }
+            uint32_t klo = 0xffffffffu, khi = 0u;
+#pragma unroll
+            for (int j = 0; j < 12; ++j)
+                if (e[j] != 0xffffffffu) { klo = min(klo, e[j]); khi = max(khi, e[j]); }
+            klo = __reduce_min_sync(FULL, klo);
+            khi = __reduce_max_sync(FULL, khi);
+            if (klo != khi && klo != 0xffffffffu) {                          // #{<= klo} = clo < K <= chi = #{<= khi}
+                uint32_t clo = 0u, chi = g_n + c;
+                klo -= 1u;
+                for (int it = 0; it < 48 && khi - klo > 1u; ++it) {
+                    const uint32_t mid = select_probe(klo, khi, clo, chi, it);
+                    uint32_t n = 0;
+#pragma unroll
+                    for (int j = 0; j < 12; ++j) n += (e[j] <= mid) ? 1u : 0u;      // 0xffffffff never counts: mid < khi <= 0xfffffffe
+                    n = __reduce_add_sync(FULL, n);
+                    if (n >= (uint32_t)K) { khi = mid; chi = n; if (n <= (uint32_t)K + 8u) break; }
+                    else { klo = mid; clo = n; }
+                }
+            }
+            uint32_t kc = 0;
+#pragma unroll
+            for (int j = 0; j < 12; ++j) kc += (e[j] != 0xffffffffu && e[j] <= khi) ? 1u : 0u;
+            uint32_t pos = kc;                                               // inclusive scan over the lanes
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL, pos, o); if (lane >= o) pos += v; }
+            const uint32_t total = __shfl_sync(FULL, pos, 31);
+            pos -= kc;
+            __syncwarp();                                                    // every lane holds its share: the list may be rewritten
+#pragma unroll
+            for (int j = 0; j < 12; ++j)
+                if (e[j] != 0xffffffffu && e[j] <= khi) { if (pos < (uint32_t)GB) Gs[pos] = e[j]; ++pos; }
             __threadfence();
-            atomicExch(&glock[qid], 0u);
+            __syncwarp();
+            const float mine = nextafterf(okey_inv(khi) + margin_src, __int_as_float(0x7f800000));
+            if (lane == 0) {
+                gcnt[q_src] = min(total, (uint32_t)GB);
+                gcut[q_src] = khi;
+                __threadfence();
+                atomicExch(&glock[q_src], 0u);
+                atomicMin(&gthr[q_src], okey(mine));
+            }
+            if (lane == src) my_thr = fminf(thr_src, mine);
         }
         __syncwarp();
-        return thr;
+        return my_thr;
     }
     const uint32_t maxg = __reduce_max_sync(FULL, gn);                 // <= GB
     const bool sel = part && gn + cnt >= (uint32_t)K;
@@ -503,11 +574,13 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
               uint64_t *__restrict__ cand, uint32_t *__restrict__ cand_cnt, uint32_t *__restrict__ gthr,
               uint32_t *__restrict__ gbest, uint32_t *__restrict__ gcnt, uint32_t *__restrict__ gcut,
               uint32_t *__restrict__ glock, uint32_t *__restrict__ flags, uint32_t *__restrict__ work_counter, int dbg,
-              unsigned long long *__restrict__ kstat)
+              uint32_t knobs, unsigned long long *__restrict__ kstat)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TensorSmem &S = *reinterpret_cast<TensorSmem *>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t part_min = knobs & 0xffffu;            // compaction: pool fill from which a lane takes part
+    const bool sparse_sel_ok = (knobs & 0x10000u) == 0u;  // merge_global: one-query-at-a-time selection when few lanes need one
 
     if (tid == 0) {
         for (int s = 0; s < NST; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 2); }   // both MMA issuers release a stage
@@ -695,13 +768,13 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
                     const uint32_t ep = *reinterpret_cast<volatile uint32_t *>(&S.cepoch[h]);
                     const bool own = __any_sync(FULL, st.cnt > (uint32_t)POOL - slack ||
                                                           (st.cnt >= 192u && st.thr == __int_as_float(0x7f800000)));
-                    const bool join = ep != my_ep && __any_sync(FULL, st.cnt >= 160u);
+                    const bool join = ep != my_ep && __any_sync(FULL, st.cnt >= max(160u, part_min));
                     if (own && ep == my_ep) { if (lane == 0) atomicAdd(&S.cepoch[h], 1u); my_ep = ep + 1; }
                     else my_ep = ep;
                     if (own || join) {
                         const long long t0 = clock64();
                         n_surv += st.cnt;
-                        const uint2 o = compact_warp(st.cnt, st.thr, st.margin, st.qid, qslot < it.nq, pool_warp, gthr, flags, KOUT, lane);
+                        const uint2 o = compact_warp(st.cnt, st.thr, st.margin, st.qid, qslot < it.nq, pool_warp, gthr, flags, KOUT, part_min, lane);
                         st.cnt = o.x; st.thr = __uint_as_float(o.y);
                         n_surv -= st.cnt;
                         c_compact += clock64() - t0; ++n_compact;
@@ -766,14 +839,14 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
                 }
                 // hand the pools to K5: lists need not be sorted, only short enough
                 if (__any_sync(FULL, st.cnt > (uint32_t)KOUT)) {
-                    const uint2 o = compact_warp(st.cnt, st.thr, st.margin, st.qid, qslot < it.nq, pool_warp, gthr, flags, KOUT, lane);
+                    const uint2 o = compact_warp(st.cnt, st.thr, st.margin, st.qid, qslot < it.nq, pool_warp, gthr, flags, KOUT, min(part_min, (uint32_t)KOUT), lane);
                     st.cnt = o.x; st.thr = __uint_as_float(o.y);
                 }
                 // tell the other chunks of these queries what this chunk found (worth it only for long sweeps)
                 const long long tm0 = clock64();
                 n_surv += st.cnt;
                 if (ntiles >= 128u && dbg == 0)
-                    st.thr = merge_global(st.cnt, st.thr, st.margin, st.qid, qslot < it.nq, pool_warp, gbest, gcnt, gcut, glock, gthr, lane);
+                    st.thr = merge_global(st.cnt, st.thr, st.margin, st.qid, qslot < it.nq, pool_warp, gbest, gcnt, gcut, glock, gthr, sparse_sel_ok, lane);
                 c_mergeonly += clock64() - tm0;
                 {
                     const uint32_t maxc = __reduce_max_sync(FULL, st.cnt);
@@ -880,12 +953,20 @@ cudaError_t launch_tile_tensor(hvs_engine *e, const float *queries_dev, const QS
     }
     static const bool pipe = [] { const char *v = getenv("HVS_K3_PIPE"); return !(v && v[0] == '0'); }();   // default: pipelined, unrolled stage scan
     static const int dbg = [] { const char *v = getenv("HVS_K3_DBG"); return v ? atoi(v) : 0; }();
+    static const uint32_t knobs = [] {
+        const char *v = getenv("HVS_K3_PARTMIN");
+        int k = v ? atoi(v) : 0;
+        uint32_t kn = (uint32_t)(k >= K && k <= POOL - 128 ? k : 256);     // measured: 256 takes the (C,T) head group from 8.9 to 5.8 Mcycles per warp
+        const char *ss = getenv("HVS_K3_SPARSE_SEL");
+        if (ss && ss[0] == '0') kn |= 0x10000u;
+        return kn;
+    }();
     auto kern = pipe ? k_tile_tensor<true> : k_tile_tensor<false>;
     kern<<<grid, NTHR, smem, e->stream>>>(queries_dev, slices_dev, items_dev + item_begin, n_items, item_q_dev,
                                           ix.xb[0].as<unsigned char>(), ix.xb[1].as<unsigned char>(), ix.xnorm_max, ix.img_scale,
                                           e->d_pool.as<uint64_t>() + (size_t)e->pool_slot * e->sm_count * QT_TENSOR * POOL, cand_dev, cand_cnt_dev, gthr_dev, e->d_gbest.as<uint32_t>(),
                                           e->d_glock.as<uint32_t>() + e->stats.m, e->d_glock.as<uint32_t>() + 2 * (size_t)e->stats.m,
-                                          e->d_glock.as<uint32_t>(), flags_dev, e->d_work_counter.as<uint32_t>() + e->work_slot, dbg, kstat);
+                                          e->d_glock.as<uint32_t>(), flags_dev, e->d_work_counter.as<uint32_t>() + e->work_slot, dbg, knobs, kstat);
     ++e->work_slot;
     if (kstat) {
         unsigned long long h[32 + 8 * 256];

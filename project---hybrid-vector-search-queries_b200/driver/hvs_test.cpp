@@ -42,6 +42,8 @@ int main(int argc, char **argv)
     if (!read_bin(query, HVS_QUERY_ROW, queries)) { std::cerr << "cannot read " << query << "\n"; return 1; }
     std::cout << "# data points:  " << nodes.size() << "\n# queries:      " << queries.size() << std::endl;
     std::vector<std::vector<uint32_t>> knn;
+    std::vector<float> dist;                       // the `.dist` table comes out of the same solve (hvs_solve_full): one index build
+    hvs_shim::want_dist = &dist;
     auto t0 = std::chrono::steady_clock::now();
     vec_query(nodes, queries, 1.0f, knn);
     auto t1 = std::chrono::steady_clock::now();
@@ -50,18 +52,7 @@ int main(int argc, char **argv)
         std::ofstream f(out, std::ios::binary);
         for (auto &r : knn) f.write(reinterpret_cast<const char *>(r.data()), (std::streamsize)(r.size() * 4));
     }
-    {   // .dist side file: sequential fp32 distances of the returned ids, on the device
-        hvs_engine *e = nullptr;
-        if (hvs_create(&e, nullptr) != HVS_OK) hvs_shim::die(nullptr, "hvs_create");
-        std::vector<float> d, q;
-        hvs_shim::flatten(nodes, HVS_DATA_ROW, d);
-        hvs_shim::flatten(queries, HVS_QUERY_ROW, q);
-        if (hvs_index_build(e, d.data(), (uint32_t)nodes.size(), 1.0f) != HVS_OK) hvs_shim::die(e, "hvs_index_build");
-        std::vector<uint32_t> ids;
-        for (auto &r : knn) ids.insert(ids.end(), r.begin(), r.end());
-        std::vector<float> dist(ids.size());
-        if (hvs_rescore(e, q.data(), (uint32_t)queries.size(), ids.data(), dist.data()) != HVS_OK) hvs_shim::die(e, "hvs_rescore");
-        hvs_destroy(e);
+    {   // .dist side file: uint32 M, then M x 100 float32 (include/io.h:50-78)
         std::ofstream f(out + ".dist", std::ios::binary);
         uint32_t m = (uint32_t)queries.size();
         f.write(reinterpret_cast<const char *>(&m), 4);

@@ -495,3 +495,36 @@ def test_many_chunks_per_slice_and_global_lists(H, oracle, check, datagen):
     ref = oracle.vec_query(d, q[pick], want_dist=False)
     p = check.compare(d, q[pick], ref, ids[pick], rtol=RTOL)
     assert p.ok and p.dist_bit_identical_rows == len(pick), p.summary()
+
+
+def test_reference_driver_impl4(H, oracle, check, datagen, tmp_path):
+    """The reference's OWN driver (src/test.cpp: its argv handling, io.h ReadBin / SaveKNN / SaveKNNFull) compiled with the
+    one-line `#elif IMPL == 4` ladder entry of INTEGRATION.md, include/hvs_vec_query.hpp behind vec_query and
+    libhvs_b200.so linked (oracle/Makefile builds it into oracle/_ref/ when /root/reference is present).  Its output.bin
+    must hold the reference's answer and its .dist file must pass the reference's own comparer against baseline.out's."""
+    import os
+    import subprocess
+    ref_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref")
+    drv, base, cmp_ = (os.path.join(ref_dir, f) for f in ("hvs_impl4.out", "baseline.out", "compare.out"))
+    if not all(os.path.exists(p) for p in (drv, base, cmp_)):
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    d = datagen.gen_data(30_000, 121, ncat=15)
+    q = datagen.gen_queries(90, 122, ncat=15)
+    dp, qp = str(tmp_path / "d.bin"), str(tmp_path / "q.bin")
+    datagen.write_bin(dp, d)
+    datagen.write_bin(qp, q)
+    outs = {}
+    for name, exe in (("impl4", drv), ("baseline", base)):
+        op = str(tmp_path / f"{name}.bin")
+        r = subprocess.run([exe, dp, qp, op], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        assert "Vector Search took" in r.stderr
+        outs[name] = op
+    ids = np.fromfile(outs["impl4"], np.uint32).reshape(len(q), 100)           # SaveKNN: headerless M x 100 uint32
+    ids_ref = np.fromfile(outs["baseline"], np.uint32).reshape(len(q), 100)
+    p = check.compare(d, q, ids_ref, ids, rtol=RTOL)
+    assert p.ok and p.dist_bit_identical_rows == len(q), p.summary()
+    for o in outs.values():                                # compare.out with NDEBUG calls two missing files "the same": check first
+        assert os.path.getsize(o) == 400 * len(q) and os.path.getsize(o + ".dist") == 4 + 400 * len(q)
+    r = subprocess.run([cmp_, outs["impl4"], outs["baseline"]], capture_output=True, text=True, timeout=120)   # it appends ".dist" itself
+    assert r.returncode == 0 and "Datasets are the same!" in (r.stdout + r.stderr), (r.stdout + r.stderr)[-500:]
