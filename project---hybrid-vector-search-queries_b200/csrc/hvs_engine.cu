@@ -171,6 +171,10 @@ extern "C" int hvs_index_build_device(hvs_engine *e, const float *rows_dev, uint
 static int solve_core(hvs_engine *e, const float *q_dev, uint32_t m, const QSlice *d_sl, const QSlice *h_sl, bool partial,
                       uint32_t *out_ids, float *out_dist, uint32_t *out_count, bool small_launched);
 
+static bool use_device_planner(const hvs_engine *e);
+static int solve_core_dev(hvs_engine *e, const float *q_dev, uint32_t m, const QSlice *d_sl, bool partial, uint32_t *out_ids,
+                          float *out_dist, uint32_t *out_count, bool small_launched);
+
 // K4s (tiny slices, a warp per query) decides on the device which queries are its own, so it is launched right behind
 // the slice search, before the host has seen a slice.  HVS_SMALL=0 switches it off (everything small takes the CTA scan).
 static uint32_t small_max()
@@ -214,9 +218,127 @@ static int solve_impl(hvs_engine *e, const float *q_dev, uint32_t m, bool partia
     ECUDA(launch_plan_search(e, q_dev, m, d_sl));
     e->stats.launches++;
     ECUDA(run_small(e, q_dev, m, d_sl, partial, out_ids, out_dist, out_count));   // runs while the slices travel to the host and are planned
+    if (use_device_planner(e)) return solve_core_dev(e, q_dev, m, d_sl, partial, out_ids, out_dist, out_count, true);
     ECUDA(cudaMemcpyAsync(e->h_slices.p, d_sl, (size_t)m * sizeof(QSlice), cudaMemcpyDeviceToHost, s));
     ECUDA(cudaStreamSynchronize(s));
     return solve_core(e, q_dev, m, d_sl, e->h_slices.as<QSlice>(), partial, out_ids, out_dist, out_count, true);
+}
+
+// ---- the solve with the planner on the device (default): no slice ever travels to the host ------------------------------
+static bool use_device_planner(const hvs_engine *e)
+{
+    static const bool host_forced = [] { const char *v = getenv("HVS_PLAN"); return v && v[0] == 'h'; }();     // HVS_PLAN=host: the host planner (A/B, debugging)
+    return !host_forced && e->index.n < (1u << 30);       // sort keys hold [class:2][arena:1][begin:nb][end:nb+1] in 64 bits
+}
+
+static int solve_core_dev(hvs_engine *e, const float *q_dev, uint32_t m, const QSlice *d_sl, bool partial, uint32_t *out_ids,
+                          float *out_dist, uint32_t *out_count, bool small_launched)
+{
+    hvs_stats &st = e->stats;
+    cudaStream_t s = e->stream;
+    if (e->flags & HVS_FLAG_MARGIN_AUDIT) {
+        ECUDA(e->d_audit.ensure(4));
+        ECUDA(cudaMemsetAsync(e->d_audit.p, 0, 4, s));
+    }
+    if (!small_launched) ECUDA(run_small(e, q_dev, m, d_sl, partial, out_ids, out_dist, out_count));
+    const bool tensor = e->index.xb[0].p != nullptr && e->index.xb[1].p != nullptr && (e->mode == HVS_MODE_AUTO || e->mode == HVS_MODE_TENSOR);
+    PlanParams defaults;
+    PlanCfg cfg{};
+    cfg.need = tensor ? defaults.tensor_min_depth : (double)QT / defaults.direct_cost_ratio;
+    cfg.min_tile_pairs = defaults.min_tile_pairs;
+    static const long long min_pairs_env = [] { const char *v = getenv("HVS_MIN_TILE_PAIRS"); return v ? atoll(v) : -1ll; }();
+    if (min_pairs_env >= 0) cfg.min_tile_pairs = (unsigned long long)min_pairs_env;
+    cfg.small_max = small_max();
+    cfg.min_tile_len = defaults.min_tile_len;
+    cfg.tile_allowed = (e->mode != HVS_MODE_DIRECT && e->index.approx_ok) ? 1u : 0u;
+    cfg.force_tile = e->mode == HVS_MODE_TENSOR ? 1u : 0u;
+    cfg.bq = tensor ? (uint32_t)QT_TENSOR : (uint32_t)QT;
+    static const uint32_t ips = [] { const char *v = getenv("HVS_ITEMS_PER_SM"); int k = v ? atoi(v) : 0; return (uint32_t)(k > 0 ? k : 16); }();
+    cfg.items_per_sm = ips;
+    cfg.sm_count = (uint32_t)e->sm_count;
+    cfg.kind = tensor ? 1u : 0u;
+    PlanHeader h{};
+    ECUDA(plan_dev_begin(e, d_sl, m, cfg, &h));                  // the one host round trip of the plan: a 128-byte header
+    st.launches += 9;
+    st.pairs = h.pairs;
+    st.pairs_tile = h.pairs_tile;
+    st.pairs_direct = h.pairs - h.pairs_tile;
+    st.n_direct = h.n_direct + h.n_small;
+    st.n_tile = h.n_tile;
+    cudaEventRecord(e->ev[3], s);
+    const uint32_t *sorted_q = e->pdev.vals.as<uint32_t>();       // tile queries [0, n_tile), CTA-scan queries [n_tile, n_tile + n_direct)
+    if (h.n_direct) {
+        ECUDA(launch_direct(e, q_dev, d_sl, sorted_q + h.n_tile, h.n_direct, partial, out_ids, out_dist, out_count));
+        st.launches++;
+    }
+    cudaEventRecord(e->ev[4], s);
+    const bool any_items = h.n_items > 0;
+    if (any_items) {
+        ECUDA(e->d_items.ensure((size_t)h.n_items * sizeof(TileItem)));
+        ECUDA(e->d_item_q.ensure((size_t)h.incid * 4));
+        ECUDA(e->d_qlists.ensure((size_t)h.incid * 4));
+        ECUDA(e->d_cand.ensure((size_t)h.incid * KOUT * 8));
+        ECUDA(e->d_cand_cnt.ensure((size_t)h.incid * 4));
+        ECUDA(e->d_flags.ensure((size_t)m * 4));
+        ECUDA(cudaMemsetAsync(e->d_flags.p, 0, (size_t)m * 4, s));
+        ECUDA(e->d_gthr.ensure((size_t)m * 4));
+        ECUDA(launch_fill_u32(e, e->d_gthr.as<uint32_t>(), 0xff800000u /* okey(+inf) */, m));
+        if (tensor) ECUDA(tile_tensor_begin(e));
+        ECUDA(plan_dev_fill(e, d_sl, h, cfg, e->d_item_q.as<uint32_t>(), e->d_items.as<TileItem>(), e->d_qlists.as<uint32_t>()));
+        st.launches += 2;
+        e->pool_slot = 0;
+        cudaEventRecord(e->evg[0], s);
+        if (tensor)
+            ECUDA(launch_tile_tensor(e, q_dev, d_sl, e->d_items.as<TileItem>(), 0, h.n_items, e->d_item_q.as<uint32_t>(), e->d_cand.as<uint64_t>(),
+                                     e->d_cand_cnt.as<uint32_t>(), e->d_gthr.as<uint32_t>(), e->d_flags.as<uint32_t>()));
+        else
+            ECUDA(launch_tile_ffma(e, q_dev, d_sl, e->d_items.as<TileItem>(), 0, h.n_items, e->d_item_q.as<uint32_t>(), e->d_cand.as<uint64_t>(),
+                                   e->d_cand_cnt.as<uint32_t>(), e->d_gthr.as<uint32_t>(), e->d_flags.as<uint32_t>(), 1.0f));
+        cudaEventRecord(e->evg[1], s);
+        st.launches++;
+        (tensor ? st.n_items_tensor : st.n_items_ffma) = h.n_items;
+        cudaEventRecord(e->ev[7], s);
+        ECUDA(launch_finalize(e, q_dev, d_sl, sorted_q, h.n_tile, e->pdev.qoff.as<uint32_t>(), e->d_qlists.as<uint32_t>(),
+                              e->d_cand.as<uint64_t>(), e->d_cand_cnt.as<uint32_t>(), e->d_flags.as<uint32_t>(), partial, tensor, out_ids,
+                              out_dist, out_count));
+        st.launches++;
+        cudaEventRecord(e->ev[8], s);
+        // queries whose candidate buffers overflowed their margin guarantee are re-solved exactly by K4: the list is built on the device
+        ECUDA(e->d_scratch.ensure((size_t)h.n_tile * 4));
+        ECUDA(plan_dev_redo(e, e->d_flags.as<uint32_t>(), h.n_tile, e->d_scratch.as<uint32_t>()));
+        st.launches++;
+        ECUDA(cudaMemcpyAsync(e->h_header.p, e->pdev.header.p, sizeof(PlanHeader), cudaMemcpyDeviceToHost, s));
+        ECUDA(cudaStreamSynchronize(s));
+        const PlanHeader h2 = *e->h_header.as<PlanHeader>();
+        st.pairs_computed = h2.pairs_computed + (h.pairs - h.pairs_tile);
+        if (h2.n_redo) {
+            ECUDA(launch_direct(e, q_dev, d_sl, e->d_scratch.as<uint32_t>(), h2.n_redo, partial, out_ids, out_dist, out_count));
+            st.launches++;
+            st.n_fallback = h2.n_redo;
+        }
+    } else {
+        st.pairs_computed = h.pairs;
+    }
+    cudaEventRecord(e->ev[9], s);
+    if (e->flags & HVS_FLAG_MARGIN_AUDIT) ECUDA(cudaMemcpyAsync(&st.margin_audit, e->d_audit.p, 4, cudaMemcpyDeviceToHost, s));
+    ECUDA(cudaStreamSynchronize(s));
+    ECUDA(cudaGetLastError());
+    const float ms_small = ev_ms(e->ev[5], e->ev[6]);
+    st.ms_plan = std::max(0.f, ev_ms(e->ev[2], e->ev[3]) - ms_small);
+    st.ms_direct = ev_ms(e->ev[3], e->ev[4]) + ms_small;
+    if (any_items) {
+        const float tile = ev_ms(e->evg[0], e->evg[1]);
+        if (tensor) st.ms_tile_tensor = tile; else st.ms_tile_ffma = tile;
+        st.ms_tile = tile;
+        st.ms_finalize = ev_ms(e->ev[7], e->ev[8]);
+    }
+    st.ms_solve_device = ev_ms(e->ev[2], e->ev[9]);
+    static const bool timeline = getenv("HVS_TIMELINE") != nullptr;
+    if (timeline)
+        fprintf(stderr, "timeline(dev planner): plan end %.2f  direct end %.2f  sweep [%.2f, %.2f]  finalize [%.2f, %.2f]  end %.2f  (R=%u, %u items, %u tile queries)\n",
+                ev_ms(e->ev[2], e->ev[3]), ev_ms(e->ev[2], e->ev[4]), any_items ? ev_ms(e->ev[2], e->evg[0]) : 0.f, any_items ? ev_ms(e->ev[2], e->evg[1]) : 0.f,
+                any_items ? ev_ms(e->ev[2], e->ev[7]) : 0.f, any_items ? ev_ms(e->ev[2], e->ev[8]) : 0.f, st.ms_solve_device, h.R, h.n_items, h.n_tile);
+    return HVS_OK;
 }
 
 static int solve_core(hvs_engine *e, const float *q_dev, uint32_t m, const QSlice *d_sl, const QSlice *h_sl, bool partial,
@@ -337,7 +459,7 @@ static int solve_core(hvs_engine *e, const float *q_dev, uint32_t m, const QSlic
         cudaEventRecord(e->ev[7], s);
         ECUDA(launch_finalize(e, q_dev, d_sl, e->d_tile_q.as<uint32_t>(), (uint32_t)P.tile_q.size(), e->d_qoff.as<uint32_t>(),
                               e->d_qlists.as<uint32_t>(), e->d_cand.as<uint64_t>(), e->d_cand_cnt.as<uint32_t>(),
-                              e->d_flags.as<uint32_t>(), partial, out_ids, out_dist, out_count));
+                              e->d_flags.as<uint32_t>(), partial, P.n_tensor > 0, out_ids, out_dist, out_count));
         st.launches++;
         cudaEventRecord(e->ev[8], s);
         // queries whose candidate buffers overflowed their margin guarantee are re-solved exactly by K4
@@ -474,8 +596,10 @@ extern "C" int hvs_solve_shard_device(hvs_engine *e, const float *queries_dev, u
         ECUDA(launch_gather_queries(e, queries_dev, d_sl_all, e->d_shard_own.as<uint32_t>(), m_own, e->d_shard_q.as<float>(),
                                     e->d_shard_sl.as<QSlice>()));
         e->stats.launches++;
-        rc = solve_core(e, e->d_shard_q.as<float>(), m_own, e->d_shard_sl.as<QSlice>(), e->h_shard_sl.data(), false, out_ids_dev,
-                        nullptr, nullptr, false);
+        rc = use_device_planner(e)
+                 ? solve_core_dev(e, e->d_shard_q.as<float>(), m_own, e->d_shard_sl.as<QSlice>(), false, out_ids_dev, nullptr, nullptr, false)
+                 : solve_core(e, e->d_shard_q.as<float>(), m_own, e->d_shard_sl.as<QSlice>(), e->h_shard_sl.data(), false, out_ids_dev,
+                              nullptr, nullptr, false);
     }
     e->stats.ms_solve_wall = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return rc;

@@ -167,6 +167,25 @@ constexpr uint64_t SHARD_QUERY_COST = 400000;   // shard_assign: fixed cost of a
 constexpr uint32_t SHARD_STRIPES = 16;          // shard_assign: segments per rank
 void shard_assign(const QSlice *slices, uint32_t m, uint32_t world, uint32_t *order, uint32_t *counts);
 void plan_build(const QSlice *slices, uint32_t m, const PlanParams &pp, Plan &out);     // begin + every group + finish
+
+// ---- the device planner (hvs_plan_dev.cu) -------------------------------------------------------------------------
+enum : uint32_t { PD_TILE = 0, PD_DIRECT = 1, PD_SMALL = 2 };   // query classes, in sort order
+struct PlanCfg {                          // by value to the planner kernels
+    double need;                          // average queries per row a tile query's slice must see
+    unsigned long long min_tile_pairs;    // tiny-job rule
+    uint32_t small_max, min_tile_len;
+    uint32_t tile_allowed, force_tile;    // mode != DIRECT && index allows approximate sweeps; mode == TENSOR
+    uint32_t bq, items_per_sm, sm_count, kind;
+};
+struct PlanHeader {                       // lives on the device; the host reads it back once per solve (and n_redo at the end)
+    unsigned long long pairs, tile_qrows, pairs_tile, pairs_computed, incid;
+    uint32_t maxend[2], nchunk[2], chunk_base[2];
+    uint32_t nchunk_total, R, n_tile, n_tile_arena0, n_direct, n_small, n_items, tiny, n_redo, pad[3];
+};
+struct PlanDev {
+    DevBuf header, diff, pref, cls, keys_in, keys, vals_in, vals, nch, qoff, cdiff, cstart, ibase, sort_tmp;
+    uint32_t nb = 0;
+};
 void plan_begin(const QSlice *slices, uint32_t m, const PlanParams &pp, Plan &out);     // classify, order, cut into groups
 void plan_group(const QSlice *slices, Plan &out, size_t g, uint32_t &item_begin, uint32_t &item_end);   // items of one group
 void plan_finish(const QSlice *slices, uint32_t m, Plan &out);                          // candidate-list CSR per query
@@ -199,6 +218,8 @@ struct hvs_engine {
     cudaEvent_t ev[12]{};
     cudaEvent_t evg[16]{};     // start/end of each group's tile launch
     hvs::Plan plan;
+    hvs::PlanDev pdev;
+    hvs::HostPinned h_header;
 };
 
 namespace hvs {
@@ -230,13 +251,18 @@ cudaError_t launch_fill_u32(hvs_engine *e, uint32_t *dst, uint32_t value, size_t
 cudaError_t launch_finalize(hvs_engine *e, const float *queries_dev, const QSlice *slices_dev,
                             const uint32_t *tile_q_dev, uint32_t n_tile_q, const uint32_t *qoff_dev,
                             const uint32_t *qlists_dev, const uint64_t *cand_dev, const uint32_t *cand_cnt_dev,
-                            uint32_t *flags_dev, bool partial, uint32_t *out_ids, float *out_dist, uint32_t *out_count);
+                            uint32_t *flags_dev, bool partial, bool tensor_lists, uint32_t *out_ids, float *out_dist, uint32_t *out_count);
 cudaError_t launch_merge_partials(hvs_engine *e, const float *queries_dev, uint32_t m, uint32_t g,
                                   const float *dist_dev, const uint32_t *ids_dev, const uint32_t *count_dev,
                                   const float *tail_rows_dev, uint32_t n_total, uint32_t *out_ids_dev);
 cudaError_t launch_rescore(hvs_engine *e, const float *queries_dev, uint32_t m, const uint32_t *ids_dev, float *out_dev,
                            const float *rows_unused);
 cudaError_t measure_ffma_peak(hvs_engine *e, uint32_t iters, float *tflops, float *mhz);
+// device planner: everything up to the header read-back (one stream sync); then the chunk lists, items and K5's list index
+cudaError_t plan_dev_begin(hvs_engine *e, const QSlice *d_sl, uint32_t m, const PlanCfg &cfg, PlanHeader *h_out);
+cudaError_t plan_dev_fill(hvs_engine *e, const QSlice *d_sl, const PlanHeader &h, const PlanCfg &cfg, uint32_t *item_q_dev,
+                          TileItem *items_dev, uint32_t *qlists_dev);
+cudaError_t plan_dev_redo(hvs_engine *e, const uint32_t *flags_dev, uint32_t n_tile, uint32_t *redo_dev);
 cudaError_t direct_init_attributes();
 cudaError_t tile_ffma_init_attributes();
 cudaError_t tile_tensor_init_attributes();

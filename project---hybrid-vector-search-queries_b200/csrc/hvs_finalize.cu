@@ -130,14 +130,14 @@ k_finalize(const float *__restrict__ queries, const QSlice *__restrict__ slices,
 
 cudaError_t launch_finalize(hvs_engine *e, const float *queries_dev, const QSlice *slices_dev, const uint32_t *tile_q_dev,
                             uint32_t n_tile_q, const uint32_t *qoff_dev, const uint32_t *qlists_dev, const uint64_t *cand_dev,
-                            const uint32_t *cand_cnt_dev, uint32_t *flags_dev, bool partial, uint32_t *out_ids,
+                            const uint32_t *cand_cnt_dev, uint32_t *flags_dev, bool partial, bool tensor_lists, uint32_t *out_ids,
                             float *out_dist, uint32_t *out_count)
 {
     if (!n_tile_q) return cudaSuccess;
     const Index &ix = e->index;
     k_finalize<<<n_tile_q, FT, 0, e->stream>>>(queries_dev, slices_dev, tile_q_dev, qoff_dev, qlists_dev, cand_dev, cand_cnt_dev,
                                                 flags_dev, ix.arena(0), ix.arena(1), ix.tail.as<float>(), ix.n_total, ix.id_offset,
-                                                ix.xnorm_max, e->plan.n_tensor ? ix.img_scale : 0.f, partial ? 1 : 0,
+                                                ix.xnorm_max, tensor_lists ? ix.img_scale : 0.f, partial ? 1 : 0,
                                                 (e->flags & HVS_FLAG_MARGIN_AUDIT) ? e->d_audit.as<uint32_t>() : nullptr, out_ids,
                                                 out_dist, out_count);
     return cudaGetLastError();
