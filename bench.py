@@ -502,6 +502,41 @@ def run_b200(args, rank, world, local_rank):
             weak = {"value": world * m / (ms_weak * 1e-3), "unit": "queries/s", "ms_per_step": ms_weak,
                     "what": f"{world} x {m} queries, each rank its own batch, no exchange"}
 
+    # the data-sharded comparison variant beside the primary one: N/world rows per GPU, the same batch on every
+    # rank, NCCL all-gather of the partial top-100s, K5 merge with the pad rule applied once -- a few steps, with parity
+    data_variant = None
+    if world > 1 and not data_sharded:
+        dlo, dhi = sharding.data_shard(n, rank, world)
+        with hvs.Engine(device=local_rank, mode=mode, stream=stream.cuda_stream, id_offset=dlo) as eds:
+            eds.index_build(d[dlo:dhi])
+            with torch.cuda.stream(stream):
+                dp_dist = torch.empty((m, 100), dtype=torch.float32, device="cuda")
+                dp_ids = torch.empty((m, 100), dtype=torch.int32, device="cuda")
+                dp_cnt = torch.empty((m,), dtype=torch.int32, device="cuda")
+                dtail = torch.from_numpy(np.ascontiguousarray(d[n - 100:])).cuda()
+                dgbuf = (torch.empty((world * m, 100), dtype=torch.float32, device="cuda"),
+                         torch.empty((world * m, 100), dtype=torch.int32, device="cuda"),
+                         torch.empty((world * m,), dtype=torch.int32, device="cuda"))
+                dout = torch.empty((m, 100), dtype=torch.int32, device="cuda")
+
+            def step_data():
+                with torch.cuda.stream(stream):
+                    for b in dgbuf:                                # poison: the merge must read THIS step's gathered lists
+                        b.view(torch.int32).fill_(0x7f7f7f7f)
+                    eds.solve_partial_device(q_dev, dp_dist, dp_ids, dp_cnt)
+                    g_dist, g_ids, g_cnt = sharding.gather_partials(dp_dist, dp_ids, dp_cnt, world, out=dgbuf)
+                    eds.merge_partials_device(q_dev, world, g_dist, g_ids, g_cnt, dtail, n, dout)
+
+            ms_data, st_data = tm.run(step_data, 3, 1, eds.stats)
+            torch.cuda.synchronize()
+            ids_data = dout.cpu().numpy().view(np.uint32).copy()
+        data_variant = {"value": m / (ms_data * 1e-3), "unit": "queries/s", "ms_per_step": ms_data, "steps": 3, "warmup": 1,
+                        "what": f"data-sharded: {world} GPUs x N/{world} rows, the same {m} queries everywhere, NCCL all-gather of "
+                                f"partial top-100s (+ match counts), K5 merge, pad rule once; gather buffers poisoned before every step",
+                        "ms_tile_rank0": st_data["ms_tile"], "ms_plan_rank0": st_data["ms_plan"], "ms_finalize_rank0": st_data["ms_finalize"]}
+        if rank == 0 and not args.no_parity:
+            data_variant["parity_vs_query_sharded"] = parity_two_families(eng, q, ids_dev, ids_data, "data-sharded vs query-sharded ids, every query")
+
     peak_tf, peak_mhz = eng.measure_ffma_peak(3)
     if rank != 0:
         eng.close()
@@ -538,6 +573,8 @@ def run_b200(args, rank, world, local_rank):
         line["per_rank"] = per_rank
         if weak:
             line["weak_scaling"] = weak
+        if data_variant:
+            line["data_sharded_variant"] = data_variant
         line["alg_tflops_whole_step"] = 200.0 * sum(r["pairs"] for r in per_rank) / (ms_step * 1e-3) / 1e12 if not data_sharded else line["alg_tflops_whole_step"]
 
     if not args.no_parity:

@@ -9,6 +9,9 @@
 // (x-q)^2 in the reference's order with unfused sub/mul/add, so distances are BIT-IDENTICAL to
 // include/baseline.hpp:53-64.  Bound: HBM (400 algorithmic bytes per pair; ~300 FP32 ops per pair
 // is 7x below the FP32 roof at that byte rate).
+#include <algorithm>
+#include <cstdlib>
+
 #include "hvs_engine.h"
 #include "hvs_topk.cuh"
 
@@ -16,6 +19,8 @@ namespace hvs {
 
 constexpr int DT = 128;      // rows per tile == threads per CTA
 constexpr int DCAP = 512;    // candidate buffer entries
+constexpr int SPLIT_MAX = 5; // most parts a long slice is cut into when only a few queries are scanned (SPLIT_MAX * K <= DCAP)
+constexpr int SPLIT_MIN_ROWS = 1024;
 
 struct DirectSmem {
     alignas(128) float x[2][DT * DIM];
@@ -24,9 +29,13 @@ struct DirectSmem {
     TopBuf<DCAP> top;
 };
 
+// split > 1 (few queries, long slices: the scan of ONE query is a serial chain of tiles, so a handful of queries leaves
+// the GPU idle): blockIdx.y cuts the slice into `split` parts, every part leaves its best 100 (distance, row) keys in
+// `scratch`, and the CTA that finishes last (a counter per query) merges them and completes the query.
 __global__ void __launch_bounds__(DT, 2)
 k_direct(const float *__restrict__ queries, const QSlice *__restrict__ slices, const uint32_t *__restrict__ q_list,
          Arena a0, Arena a1, const float *__restrict__ tail, uint32_t n_total, uint32_t id_offset, int partial,
+         uint32_t split, uint64_t *__restrict__ scratch, uint32_t *__restrict__ counters, uint32_t skip_max,
          uint32_t *__restrict__ out_ids, float *__restrict__ out_dist, uint32_t *__restrict__ out_count)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -35,7 +44,13 @@ k_direct(const float *__restrict__ queries, const QSlice *__restrict__ slices, c
     const uint32_t q = q_list ? q_list[blockIdx.x] : blockIdx.x;
     const QSlice sl = slices[q];
     const Arena A = sl.arena == ARENA_T ? a0 : a1;
-    const uint32_t len = sl.end - sl.begin;
+    const uint32_t len_all = sl.end - sl.begin;
+    if (len_all <= skip_max && skip_max) return;             // K4s has this query (launches over ALL queries, no planner)
+    const uint32_t parts = (split > 1 && len_all >= (uint32_t)SPLIT_MIN_ROWS) ? split : 1u;    // short slices are not worth cutting
+    if (blockIdx.y >= parts) return;
+    const uint32_t seg = parts > 1 ? (len_all + parts - 1) / parts : len_all;
+    const uint32_t begin = min(sl.end, sl.begin + blockIdx.y * seg);
+    const uint32_t len = min(sl.end - begin, seg);
     const uint32_t ntiles = (len + DT - 1) / DT;
 
     if (tid == 0) {
@@ -52,7 +67,7 @@ k_direct(const float *__restrict__ queries, const QSlice *__restrict__ slices, c
         uint32_t rows = min((uint32_t)DT, len - it * DT);
         uint32_t bytes = rows * ROW_BYTES;
         mbar_expect_tx(&S.bar[it & 1], bytes);
-        bulk_g2s(S.x[it & 1], A.x + (size_t)(sl.begin + it * DT) * DIM, bytes, &S.bar[it & 1]);
+        bulk_g2s(S.x[it & 1], A.x + (size_t)(begin + it * DT) * DIM, bytes, &S.bar[it & 1]);
     };
     if (tid == 0) {
         if (ntiles > 0) issue(0);
@@ -64,14 +79,35 @@ k_direct(const float *__restrict__ queries, const QSlice *__restrict__ slices, c
         bool high = false;                     // one of my pushes took a slot past the compaction mark
         if ((uint32_t)tid < rows) {
             float d = ref_dist_row(S.x[it & 1] + tid * DIM, S.q);
-            if (d < S.top.thr) high = S.top.push(d, sl.begin + it * DT + tid) >= (uint32_t)(DCAP - DT);
+            if (d < S.top.thr) high = S.top.push(d, begin + it * DT + tid) >= (uint32_t)(DCAP - DT);
         }
         const bool need = __syncthreads_or(high);   // tile consumed, pushes visible; the decision is block-uniform
         if (tid == 0 && it + 2 < ntiles) issue(it + 2);
         if (need) S.top.compact(tid, DT, 0.f, K);
     }
     __syncthreads();
-    finish_query(S.top, S.q, A, len, tail, n_total, id_offset, q, partial != 0, out_ids, out_dist, out_count, tid, DT);
+    if (parts > 1) {
+        // this part's best K keys -> scratch; the last part to arrive merges all of them
+        if ((int)S.top.cnt > K) S.top.compact(tid, DT, 0.f, K);
+        const uint32_t c = min(S.top.cnt, (uint32_t)K);
+        uint64_t *mine = scratch + ((size_t)blockIdx.x * split + blockIdx.y) * K;
+        for (uint32_t i = tid; i < (uint32_t)K; i += DT) mine[i] = i < c ? S.top.cand[i] : KEY_INF;
+        __threadfence();
+        __syncthreads();
+        __shared__ uint32_t s_last;
+        if (tid == 0) s_last = atomicAdd(&counters[blockIdx.x], 1u) == parts - 1u ? 1u : 0u;
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        const uint64_t *all = scratch + (size_t)blockIdx.x * split * K;
+        static_assert(SPLIT_MAX * K <= DCAP, "the merge loads every part's list into the candidate buffer");
+        for (uint32_t i = tid; i < parts * (uint32_t)K; i += DT) S.top.cand[i] = __ldcg(all + i);
+        __syncthreads();
+        if (tid == 0) { S.top.cnt = parts * (uint32_t)K; S.top.thr = __int_as_float(0x7f800000); }
+        __syncthreads();
+        S.top.compact(tid, DT, 0.f, K);        // sorts: real keys first (len_all >= SPLIT_MIN_ROWS > K of them), KEY_INF fillers last; keeps K
+    }
+    finish_query(S.top, S.q, A, len_all, tail, n_total, id_offset, q, partial != 0, out_ids, out_dist, out_count, tid, DT);
 }
 
 // ---- K4s: tiny slices, one WARP per query ---------------------------------------------------------------------------
@@ -203,13 +239,29 @@ cudaError_t direct_init_attributes()     // per device; called by hvs_create wit
 }
 
 cudaError_t launch_direct(hvs_engine *e, const float *queries_dev, const QSlice *slices_dev, const uint32_t *q_list_dev,
-                          uint32_t nq, bool partial, uint32_t *out_ids, float *out_dist, uint32_t *out_count)
+                          uint32_t nq, bool partial, uint32_t *out_ids, float *out_dist, uint32_t *out_count, uint32_t skip_max)
 {
     if (!nq) return cudaSuccess;
     const int smem = (int)sizeof(DirectSmem);
     const Index &ix = e->index;
-    k_direct<<<nq, DT, smem, e->stream>>>(queries_dev, slices_dev, q_list_dev, ix.arena(0), ix.arena(1),
-                                           ix.tail.as<float>(), ix.n_total, ix.id_offset, partial ? 1 : 0, out_ids, out_dist, out_count);
+    // few queries: cut long slices so that the scan of a query is not one serial chain on one SM (2 CTAs fit an SM)
+    uint32_t split = 1;
+    static const bool split_ok = [] { const char *v = getenv("HVS_DIRECT_SPLIT"); return !(v && v[0] == '0'); }();
+    if (split_ok && nq <= 2u * (uint32_t)e->sm_count) split = std::max<uint32_t>(1u, std::min<uint32_t>(SPLIT_MAX, (uint32_t)(4 * e->sm_count) / nq));
+    uint64_t *scratch = nullptr;
+    uint32_t *counters = nullptr;
+    if (split > 1) {
+        const size_t sb = (size_t)nq * split * K * 8;
+        cudaError_t c = e->d_split.ensure(sb + (size_t)nq * 4);
+        if (c != cudaSuccess) return c;
+        scratch = e->d_split.as<uint64_t>();
+        counters = reinterpret_cast<uint32_t *>(e->d_split.as<unsigned char>() + sb);
+        c = cudaMemsetAsync(counters, 0, (size_t)nq * 4, e->stream);
+        if (c != cudaSuccess) return c;
+    }
+    k_direct<<<dim3(nq, split), DT, smem, e->stream>>>(queries_dev, slices_dev, q_list_dev, ix.arena(0), ix.arena(1),
+                                                       ix.tail.as<float>(), ix.n_total, ix.id_offset, partial ? 1 : 0, split, scratch, counters,
+                                                       skip_max, out_ids, out_dist, out_count);
     return cudaGetLastError();
 }
 

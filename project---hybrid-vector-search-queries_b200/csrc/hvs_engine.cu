@@ -115,7 +115,7 @@ extern "C" void hvs_destroy(hvs_engine *e)
     ix.keys_t.release(); ix.keys_ct.release(); ix.tail.release(); ix.inv_t.release(); ix.outl[0].release(); ix.outl[1].release();
     DevBuf *bufs[] = {&e->d_queries, &e->d_out, &e->d_slices, &e->d_direct_q, &e->d_items, &e->d_item_q, &e->d_tile_q,
                       &e->d_qoff, &e->d_qlists, &e->d_cand, &e->d_cand_cnt, &e->d_scratch, &e->d_flags, &e->d_gthr, &e->d_pool, &e->d_gbest, &e->d_glock,
-                      &e->d_work_counter, &e->d_rescore_ids, &e->d_rescore_out, &e->d_audit, &e->d_shard_q, &e->d_shard_sl, &e->d_shard_own};
+                      &e->d_work_counter, &e->d_rescore_ids, &e->d_rescore_out, &e->d_audit, &e->d_shard_q, &e->d_shard_sl, &e->d_shard_own, &e->d_split, &e->d_k1acc};
     for (DevBuf *b : bufs) b->release();
     e->h_slices.release(); e->h_flags.release(); e->h_stage_own.release(); e->h_stage.release(); e->h_ingest[0].release(); e->h_ingest[1].release();
     for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
@@ -257,6 +257,27 @@ static int solve_core_dev(hvs_engine *e, const float *q_dev, uint32_t m, const Q
     cfg.items_per_sm = ips;
     cfg.sm_count = (uint32_t)e->sm_count;
     cfg.kind = tensor ? 1u : 0u;
+    // A job that cannot reach the tiny-job bound whatever its slices are (m x n pairs at most) needs no plan at all:
+    // K4s took the small slices, the CTA scan takes every other query, nothing is read back but the pair count.
+    if (small_launched && !cfg.force_tile && (unsigned long long)m * e->index.n < cfg.min_tile_pairs) {
+        cudaEventRecord(e->ev[3], s);
+        ECUDA(launch_direct(e, q_dev, d_sl, nullptr, m, partial, out_ids, out_dist, out_count, small_max() ? small_max() : 0u));
+        st.launches++;
+        cudaEventRecord(e->ev[4], s);
+        cudaEventRecord(e->ev[9], s);
+        ECUDA(e->h_header.ensure(sizeof(PlanHeader)));
+        ECUDA(cudaMemcpyAsync(e->h_header.p, e->d_k1acc.p, 16, cudaMemcpyDeviceToHost, s));
+        ECUDA(cudaStreamSynchronize(s));
+        ECUDA(cudaGetLastError());
+        const unsigned long long *acc = e->h_header.as<unsigned long long>();
+        st.pairs = st.pairs_direct = st.pairs_computed = acc[0];
+        st.n_direct = m;
+        const float ms_small = ev_ms(e->ev[5], e->ev[6]);
+        st.ms_plan = std::max(0.f, ev_ms(e->ev[2], e->ev[3]) - ms_small);
+        st.ms_direct = ev_ms(e->ev[3], e->ev[4]) + ms_small;
+        st.ms_solve_device = ev_ms(e->ev[2], e->ev[9]);
+        return HVS_OK;
+    }
     PlanHeader h{};
     ECUDA(plan_dev_begin(e, d_sl, m, cfg, &h));                  // the one host round trip of the plan: a 128-byte header
     st.launches += 9;
@@ -574,32 +595,53 @@ extern "C" int hvs_solve_shard_device(hvs_engine *e, const float *queries_dev, u
     QSlice *d_sl_all = e->d_slices.as<QSlice>();
     cudaEventRecord(e->ev[2], s);
     ECUDA(launch_plan_search(e, queries_dev, m, d_sl_all));                 // every rank resolves ALL predicates (two binary searches each)
-    ECUDA(cudaMemcpyAsync(e->h_slices.p, d_sl_all, (size_t)m * sizeof(QSlice), cudaMemcpyDeviceToHost, s));
-    ECUDA(cudaStreamSynchronize(s));
-    const QSlice *h_all = e->h_slices.as<QSlice>();
-    shard_assign(h_all, m, world, out_order_host, out_counts_host);        // the same on every rank
-    uint32_t off = 0;
-    for (uint32_t r = 0; r < rank; ++r) off += out_counts_host[r];
-    const uint32_t m_own = out_counts_host[rank];
-    const uint32_t *own = out_order_host + off;
+    const uint32_t stripes = shard_stripes(m, world);
+    // the assignment runs on the device unless its 64-bit cost arithmetic could overflow (m x n beyond ~10^15) or the host planner is forced
+    const bool on_device = use_device_planner(e) && (double)m * ((double)e->index.n + (double)SHARD_QUERY_COST) * world * stripes < 9.0e18;
+    const uint32_t *own_dev = nullptr;
+    uint32_t off = 0, m_own = 0;
+    if (on_device) {
+        uint32_t *order_dev = nullptr, *counts_dev = nullptr;
+        ECUDA(shard_assign_dev(e, d_sl_all, m, world, stripes, &order_dev, &counts_dev));
+        ECUDA(e->h_stage_own.ensure((size_t)m * 4 + 256 * 4));
+        uint32_t *h_order = e->h_stage_own.as<uint32_t>(), *h_counts = h_order + m;
+        ECUDA(cudaMemcpyAsync(h_order, order_dev, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
+        ECUDA(cudaMemcpyAsync(h_counts, counts_dev, (size_t)world * 4, cudaMemcpyDeviceToHost, s));
+        ECUDA(cudaStreamSynchronize(s));
+        std::memcpy(out_order_host, h_order, (size_t)m * 4);
+        std::memcpy(out_counts_host, h_counts, (size_t)world * 4);
+        for (uint32_t r = 0; r < rank; ++r) off += out_counts_host[r];
+        m_own = out_counts_host[rank];
+        own_dev = order_dev + off;
+    } else {
+        ECUDA(cudaMemcpyAsync(e->h_slices.p, d_sl_all, (size_t)m * sizeof(QSlice), cudaMemcpyDeviceToHost, s));
+        ECUDA(cudaStreamSynchronize(s));
+        shard_assign(e->h_slices.as<QSlice>(), m, world, out_order_host, out_counts_host);        // the same on every rank
+        for (uint32_t r = 0; r < rank; ++r) off += out_counts_host[r];
+        m_own = out_counts_host[rank];
+        ECUDA(e->d_shard_own.ensure((size_t)m_own * 4 + 16));
+        ECUDA(e->h_stage_own.ensure((size_t)m_own * 4 + 16));
+        std::memcpy(e->h_stage_own.p, out_order_host + off, (size_t)m_own * 4);
+        ECUDA(cudaMemcpyAsync(e->d_shard_own.p, e->h_stage_own.p, (size_t)m_own * 4, cudaMemcpyHostToDevice, s));
+        own_dev = e->d_shard_own.as<uint32_t>();
+    }
     reset_solve_stats(e, m_own);
-    e->stats.launches = 1;
+    e->stats.launches = on_device ? 6 : 1;
     if (m_own) {
-        e->h_shard_sl.resize(m_own);
-        for (uint32_t i = 0; i < m_own; ++i) e->h_shard_sl[i] = h_all[own[i]];
-        ECUDA(e->d_shard_own.ensure((size_t)m_own * 4));
         ECUDA(e->d_shard_q.ensure((size_t)m_own * QROW * 4));
         ECUDA(e->d_shard_sl.ensure((size_t)m_own * sizeof(QSlice)));
-        ECUDA(e->h_stage_own.ensure((size_t)m_own * 4));
-        std::memcpy(e->h_stage_own.p, own, (size_t)m_own * 4);
-        ECUDA(cudaMemcpyAsync(e->d_shard_own.p, e->h_stage_own.p, (size_t)m_own * 4, cudaMemcpyHostToDevice, s));
-        ECUDA(launch_gather_queries(e, queries_dev, d_sl_all, e->d_shard_own.as<uint32_t>(), m_own, e->d_shard_q.as<float>(),
-                                    e->d_shard_sl.as<QSlice>()));
+        ECUDA(launch_gather_queries(e, queries_dev, d_sl_all, own_dev, m_own, e->d_shard_q.as<float>(), e->d_shard_sl.as<QSlice>()));
         e->stats.launches++;
-        rc = use_device_planner(e)
-                 ? solve_core_dev(e, e->d_shard_q.as<float>(), m_own, e->d_shard_sl.as<QSlice>(), false, out_ids_dev, nullptr, nullptr, false)
-                 : solve_core(e, e->d_shard_q.as<float>(), m_own, e->d_shard_sl.as<QSlice>(), e->h_shard_sl.data(), false, out_ids_dev,
-                              nullptr, nullptr, false);
+        if (use_device_planner(e))
+            rc = solve_core_dev(e, e->d_shard_q.as<float>(), m_own, e->d_shard_sl.as<QSlice>(), false, out_ids_dev, nullptr, nullptr, false);
+        else {
+            const QSlice *h_all = e->h_slices.as<QSlice>();
+            const uint32_t *own = out_order_host + off;
+            e->h_shard_sl.resize(m_own);
+            for (uint32_t i = 0; i < m_own; ++i) e->h_shard_sl[i] = h_all[own[i]];
+            rc = solve_core(e, e->d_shard_q.as<float>(), m_own, e->d_shard_sl.as<QSlice>(), e->h_shard_sl.data(), false, out_ids_dev,
+                            nullptr, nullptr, false);
+        }
     }
     e->stats.ms_solve_wall = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return rc;

@@ -184,6 +184,7 @@ struct PlanHeader {                       // lives on the device; the host reads
 };
 struct PlanDev {
     DevBuf header, diff, pref, cls, keys_in, keys, vals_in, vals, nch, qoff, cdiff, cstart, ibase, sort_tmp;
+    DevBuf sa_owner_in, sa_owner, sa_order, sa_counts;     // query sharding
     uint32_t nb = 0;
 };
 void plan_begin(const QSlice *slices, uint32_t m, const PlanParams &pp, Plan &out);     // classify, order, cut into groups
@@ -211,7 +212,7 @@ struct hvs_engine {
     hvs_stats stats{};
     // per-solve scratch (grow-only)
     hvs::DevBuf d_queries, d_out, d_slices, d_direct_q, d_items, d_item_q, d_tile_q, d_qoff, d_qlists;
-    hvs::DevBuf d_cand, d_cand_cnt, d_scratch, d_flags, d_gthr, d_pool, d_gbest, d_glock, d_work_counter, d_rescore_ids, d_rescore_out, d_audit, d_shard_q, d_shard_sl, d_shard_own;
+    hvs::DevBuf d_cand, d_cand_cnt, d_scratch, d_flags, d_gthr, d_pool, d_gbest, d_glock, d_work_counter, d_rescore_ids, d_rescore_out, d_audit, d_shard_q, d_shard_sl, d_shard_own, d_split, d_k1acc;
     std::vector<hvs::QSlice> h_shard_sl;
     std::vector<uint32_t> h_shard_order, h_shard_counts;
     hvs::HostPinned h_slices, h_flags, h_stage_own, h_stage, h_ingest[2];
@@ -225,7 +226,7 @@ struct hvs_engine {
 namespace hvs {
 // each returns cudaSuccess or the failing error (message left in e->err)
 cudaError_t index_build_device(hvs_engine *e, const float *rows_dev, uint32_t n_total, float sample_proportion);
-cudaError_t launch_plan_search(hvs_engine *e, const float *queries_dev, uint32_t m, QSlice *slices_dev);
+cudaError_t launch_plan_search(hvs_engine *e, const float *queries_dev, uint32_t m, QSlice *slices_dev);   // also zeroes and fills e->d_k1acc: {pairs, small queries}
 // q_sub[i] = queries[own[i]], sl_sub[i] = slices[own[i]]  (the queries a rank owns, made contiguous)
 cudaError_t launch_gather_queries(hvs_engine *e, const float *queries_dev, const QSlice *slices_dev, const uint32_t *own_dev,
                                   uint32_t n_own, float *q_sub, QSlice *sl_sub);
@@ -234,7 +235,7 @@ cudaError_t launch_gather_queries(hvs_engine *e, const float *queries_dev, const
 // partial == true : writes out_dist/out_ids (ascending, unused = +inf/0xFFFFFFFF) and out_count, no pad.
 cudaError_t launch_direct(hvs_engine *e, const float *queries_dev, const QSlice *slices_dev,
                           const uint32_t *q_list_dev, uint32_t nq, bool partial,
-                          uint32_t *out_ids, float *out_dist, uint32_t *out_count);
+                          uint32_t *out_ids, float *out_dist, uint32_t *out_count, uint32_t skip_max = 0);
 // K4s: every query of q_list (or 0..nq-1) whose slice has at most small_max rows, one warp each; longer ones are skipped.
 cudaError_t launch_small(hvs_engine *e, const float *queries_dev, const QSlice *slices_dev, const uint32_t *q_list_dev,
                          uint32_t nq, uint32_t small_max, bool partial, uint32_t *out_ids, float *out_dist, uint32_t *out_count);
@@ -263,6 +264,9 @@ cudaError_t plan_dev_begin(hvs_engine *e, const QSlice *d_sl, uint32_t m, const 
 cudaError_t plan_dev_fill(hvs_engine *e, const QSlice *d_sl, const PlanHeader &h, const PlanCfg &cfg, uint32_t *item_q_dev,
                           TileItem *items_dev, uint32_t *qlists_dev);
 cudaError_t plan_dev_redo(hvs_engine *e, const uint32_t *flags_dev, uint32_t n_tile, uint32_t *redo_dev);
+cudaError_t shard_assign_dev(hvs_engine *e, const QSlice *d_sl, uint32_t m, uint32_t world, uint32_t stripes,
+                             uint32_t **order_dev, uint32_t **counts_dev);
+uint32_t shard_stripes(uint32_t m, uint32_t world);
 cudaError_t direct_init_attributes();
 cudaError_t tile_ffma_init_attributes();
 cudaError_t tile_tensor_init_attributes();

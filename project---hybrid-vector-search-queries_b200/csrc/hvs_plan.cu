@@ -39,7 +39,8 @@ __device__ __forceinline__ uint32_t upper_bound_dev(const T *__restrict__ a, uin
 
 // One warp per query: lane 0 decodes and searches, the warp computes ||q||^2.
 __global__ void k_plan_search(const float *__restrict__ queries, uint32_t m, const uint32_t *__restrict__ keys_t,
-                              const uint64_t *__restrict__ keys_ct, uint32_t n, QSlice *__restrict__ out)
+                              const uint64_t *__restrict__ keys_ct, uint32_t n, uint32_t small_max, QSlice *__restrict__ out,
+                              unsigned long long *__restrict__ k1acc /* {sum of max(len, K), queries with len <= small_max} */)
 {
     uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (q >= m) return;
@@ -75,14 +76,21 @@ __global__ void k_plan_search(const float *__restrict__ queries, uint32_t m, con
     }                                             // any other type: no branch taken, empty set
     if (s.end < s.begin) s.end = s.begin;         // l > r
     out[q] = s;
+    const uint32_t len = s.end - s.begin;
+    atomicAdd(&k1acc[0], (unsigned long long)(len > (uint32_t)K ? len : (uint32_t)K));
+    if (len <= small_max) atomicAdd(&k1acc[1], 1ull);
 }
 
 cudaError_t launch_plan_search(hvs_engine *e, const float *queries_dev, uint32_t m, QSlice *slices_dev)
 {
     if (!m) return cudaSuccess;
     const Index &ix = e->index;
+    cudaError_t c = e->d_k1acc.ensure(16);
+    if (c == cudaSuccess) c = cudaMemsetAsync(e->d_k1acc.p, 0, 16, e->stream);
+    if (c != cudaSuccess) return c;
     unsigned blocks = (unsigned)(((size_t)m * 32 + 255) / 256);
-    k_plan_search<<<blocks, 256, 0, e->stream>>>(queries_dev, m, ix.keys_t.as<uint32_t>(), ix.keys_ct.as<uint64_t>(), ix.n, slices_dev);
+    k_plan_search<<<blocks, 256, 0, e->stream>>>(queries_dev, m, ix.keys_t.as<uint32_t>(), ix.keys_ct.as<uint64_t>(), ix.n, SMALL_MAX, slices_dev,
+                                                 e->d_k1acc.as<unsigned long long>());
     return cudaGetLastError();
 }
 
@@ -499,6 +507,13 @@ void plan_finish(const QSlice *sl, uint32_t m, Plan &P)
 // together in runs.  Pure function of the slices: every rank computes the same answer without talking to the others.
 //   order  : all m query indices, rank-major (rank 0's queries first), each rank's in (arena, begin, end) order
 //   counts : queries per rank
+uint32_t shard_stripes(uint32_t m, uint32_t world)
+{
+    uint32_t stripes = SHARD_STRIPES;
+    while (stripes > 1 && (uint64_t)world * stripes * 64 > m) stripes >>= 1;      // small batches: fewer, longer runs
+    return stripes;
+}
+
 void shard_assign(const QSlice *sl, uint32_t m, uint32_t world, uint32_t *order, uint32_t *counts)
 {
     if (world == 0) return;
@@ -511,17 +526,15 @@ void shard_assign(const QSlice *sl, uint32_t m, uint32_t world, uint32_t *order,
     auto cost_of = [&](uint32_t i) { return (uint64_t)std::max(sl[i].end - sl[i].begin, (uint32_t)K) + SHARD_QUERY_COST; };
     uint64_t total = 0;
     for (uint32_t i = 0; i < m; ++i) total += cost_of(i);
-    uint32_t stripes = SHARD_STRIPES;
-    while (stripes > 1 && (uint64_t)world * stripes * 64 > m) stripes >>= 1;      // small batches: fewer, longer runs
-    const uint64_t nseg = (uint64_t)world * stripes;
+    const uint64_t nseg = (uint64_t)world * shard_stripes(m, world);
+    const bool fits64 = (unsigned __int128)total * nseg < ((unsigned __int128)1 << 63);   // then plain 64-bit arithmetic (what the device kernel uses)
     std::vector<uint8_t> owner(m);
     uint64_t cum = 0;
     for (int a = 0; a < 2; ++a)
         for (const auto &kv : keys[a]) {
             const uint64_t c = cost_of(kv.second);
             // the segment that holds the midpoint of this query's cost interval
-            unsigned __int128 pos = (unsigned __int128)(cum + c / 2) * nseg;
-            uint64_t seg = (uint64_t)(pos / total);
+            uint64_t seg = fits64 ? (cum + c / 2) * nseg / total : (uint64_t)((unsigned __int128)(cum + c / 2) * nseg / total);
             if (seg >= nseg) seg = nseg - 1;
             owner[kv.second] = (uint8_t)(seg % world);
             cum += c;

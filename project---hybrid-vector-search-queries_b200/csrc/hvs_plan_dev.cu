@@ -341,8 +341,94 @@ __global__ void k_pd_redo(const uint32_t *__restrict__ flags, const uint32_t *__
     if (flags[q]) redo[atomicAdd(&H->n_redo, 1u)] = q;
 }
 
+// ---- query sharding on the device (same rule as shard_assign in hvs_plan.cu) ---------------------------------------------
+__global__ void k_sa_keys(const QSlice *__restrict__ sl, uint32_t m, uint32_t nb, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const QSlice s = sl[i];
+    keys[i] = ((uint64_t)(s.arena & 1u) << (2 * nb + 1)) | ((uint64_t)s.begin << (nb + 1)) | (uint64_t)s.end;
+    vals[i] = i;
+}
+
+// One CTA: cumulative cost along the (arena, begin, end) order -> segment -> owner rank; queries per rank.
+__global__ void __launch_bounds__(SCAN_T) k_sa_assign(const QSlice *__restrict__ sl, const uint32_t *__restrict__ vals, uint32_t m,
+                                                      uint32_t world, uint32_t stripes, unsigned long long query_cost,
+                                                      uint32_t *__restrict__ owner /* [m], by sorted position */,
+                                                      uint32_t *__restrict__ counts /* [world] */)
+{
+    __shared__ unsigned long long sm64[33];
+    __shared__ uint32_t scnt[256];
+    if (threadIdx.x < 256) scnt[threadIdx.x] = 0;
+    const uint32_t per = (m + SCAN_T - 1) / SCAN_T;
+    const uint32_t t0 = min(m, threadIdx.x * per), t1 = min(m, t0 + per);
+    auto cost_of = [&](uint32_t t) {
+        const QSlice s = sl[vals[t]];
+        const uint32_t len = s.end - s.begin;
+        return (unsigned long long)(len > (uint32_t)K ? len : (uint32_t)K) + query_cost;
+    };
+    unsigned long long mine = 0;
+    for (uint32_t t = t0; t < t1; ++t) mine += cost_of(t);
+    unsigned long long total;
+    unsigned long long cum = block_excl_scan<unsigned long long>(mine, &total, sm64);      // has the barriers scnt needs
+    const unsigned long long nseg = (unsigned long long)world * stripes;
+    for (uint32_t t = t0; t < t1; ++t) {
+        const unsigned long long c = cost_of(t);
+        unsigned long long seg = (cum + c / 2) * nseg / total;       // the segment that holds the midpoint of this query's cost interval
+        if (seg >= nseg) seg = nseg - 1;
+        const uint32_t o = (uint32_t)(seg % world);
+        owner[t] = o;
+        atomicAdd(&scnt[o], 1u);
+        cum += c;
+    }
+    __syncthreads();
+    if (threadIdx.x < world) counts[threadIdx.x] = scnt[threadIdx.x];
+}
+
 // ---- host side -------------------------------------------------------------------------------------------------------
 #define PDCK(call) do { cudaError_t _c = (call); if (_c != cudaSuccess) return _c; } while (0)
+
+// order_dev: all m query indices rank-major (each rank's in (arena, begin, end) order); counts_dev: [world].  Both stay on the
+// device (the caller copies what it needs).  Precondition: (sum of costs) * world * stripes < 2^64 (checked by the caller).
+cudaError_t shard_assign_dev(hvs_engine *e, const QSlice *d_sl, uint32_t m, uint32_t world, uint32_t stripes,
+                             uint32_t **order_dev, uint32_t **counts_dev)
+{
+    cudaStream_t s = e->stream;
+    PlanDev &P = e->pdev;
+    const uint32_t n = e->index.n;
+    uint32_t nb = 1;
+    while ((1ull << nb) <= (uint64_t)n) ++nb;
+    PDCK(P.keys_in.ensure((size_t)m * 8));
+    PDCK(P.keys.ensure((size_t)m * 8));
+    PDCK(P.vals_in.ensure((size_t)m * 4));
+    PDCK(P.vals.ensure((size_t)m * 4));
+    PDCK(P.sa_owner_in.ensure((size_t)m * 4));
+    PDCK(P.sa_owner.ensure((size_t)m * 4));
+    PDCK(P.sa_order.ensure((size_t)m * 4));
+    PDCK(P.sa_counts.ensure(256 * 4));
+    const unsigned gb = (m + 255) / 256;
+    k_sa_keys<<<gb, 256, 0, s>>>(d_sl, m, nb, P.keys_in.as<uint64_t>(), P.vals_in.as<uint32_t>());
+    size_t tb1 = 0, tb2 = 0;
+    const int end_bit = (int)(2 * nb + 2);
+    PDCK(cub::DeviceRadixSort::SortPairs(nullptr, tb1, P.keys_in.as<uint64_t>(), P.keys.as<uint64_t>(), P.vals_in.as<uint32_t>(),
+                                         P.vals.as<uint32_t>(), (int)m, 0, end_bit, s));
+    PDCK(cub::DeviceRadixSort::SortPairs(nullptr, tb2, P.sa_owner_in.as<uint32_t>(), P.sa_owner.as<uint32_t>(), P.vals.as<uint32_t>(),
+                                         P.sa_order.as<uint32_t>(), (int)m, 0, 8, s));
+    PDCK(P.sort_tmp.ensure(tb1 > tb2 ? tb1 : tb2));
+    size_t tb = P.sort_tmp.cap;
+    PDCK(cub::DeviceRadixSort::SortPairs(P.sort_tmp.p, tb, P.keys_in.as<uint64_t>(), P.keys.as<uint64_t>(), P.vals_in.as<uint32_t>(),
+                                         P.vals.as<uint32_t>(), (int)m, 0, end_bit, s));
+    k_sa_assign<<<1, SCAN_T, 0, s>>>(d_sl, P.vals.as<uint32_t>(), m, world, stripes, SHARD_QUERY_COST, P.sa_owner_in.as<uint32_t>(),
+                                     P.sa_counts.as<uint32_t>());
+    tb = P.sort_tmp.cap;
+    // stable sort by owner: rank-major, each rank's queries keep the (arena, begin, end) order
+    PDCK(cub::DeviceRadixSort::SortPairs(P.sort_tmp.p, tb, P.sa_owner_in.as<uint32_t>(), P.sa_owner.as<uint32_t>(), P.vals.as<uint32_t>(),
+                                         P.sa_order.as<uint32_t>(), (int)m, 0, 8, s));
+    PDCK(cudaGetLastError());
+    *order_dev = P.sa_order.as<uint32_t>();
+    *counts_dev = P.sa_counts.as<uint32_t>();
+    return cudaSuccess;
+}
 
 cudaError_t plan_dev_begin(hvs_engine *e, const QSlice *d_sl, uint32_t m, const PlanCfg &cfg, PlanHeader *h_out)
 {

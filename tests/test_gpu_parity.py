@@ -528,3 +528,32 @@ def test_reference_driver_impl4(H, oracle, check, datagen, tmp_path):
         assert os.path.getsize(o) == 400 * len(q) and os.path.getsize(o + ".dist") == 4 + 400 * len(q)
     r = subprocess.run([cmp_, outs["impl4"], outs["baseline"]], capture_output=True, text=True, timeout=120)   # it appends ".dist" itself
     assert r.returncode == 0 and "Datasets are the same!" in (r.stdout + r.stderr), (r.stdout + r.stderr)[-500:]
+
+
+def test_tiny_job_fast_path(H, oracle, check, datagen, tmp_path):
+    """A job that cannot reach the planner's tiny-job bound (m x n < 4x10^6 pairs; BASELINE configs[0]) skips the planner
+    altogether: slice search, K4s for the small slices, one (split) CTA scan for the rest.  The test-suite switches
+    that rule off (HVS_MIN_TILE_PAIRS=0, read once per process), so this runs in a fresh interpreter without it."""
+    import os
+    import subprocess
+    import sys
+    d = datagen.gen_data(9_000, 131, ncat=10)
+    q = datagen.gen_queries(120, 132, ncat=10)
+    np.savez(tmp_path / "in.npz", d=d, q=q)
+    code = (
+        "import importlib, sys, numpy as np\n"
+        f"sys.path.insert(0, {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r})\n"
+        "H = importlib.import_module('project---hybrid-vector-search-queries_b200')\n"
+        f"z = np.load({str(tmp_path / 'in.npz')!r})\n"
+        "with H.Engine(mode=H.MODE_AUTO) as e:\n"
+        "    e.index_build(z['d']); ids = e.solve(z['q']); st = e.stats()\n"
+        f"np.savez({str(tmp_path / 'out.npz')!r}, ids=ids, n_tile=st['n_tile'], n_direct=st['n_direct'], launches=st['launches'], pairs=st['pairs'])\n")
+    env = {k: v for k, v in os.environ.items() if k != "HVS_MIN_TILE_PAIRS"}
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = np.load(tmp_path / "out.npz")
+    assert int(out["n_tile"]) == 0 and int(out["n_direct"]) == len(q) and int(out["launches"]) <= 3, dict(out)
+    ref, nmatch = oracle.vec_query(d, q, want_dist=False, want_nmatch=True)
+    assert int(out["pairs"]) == int(np.maximum(nmatch, 100).sum())
+    p = check.compare(d, q, ref, out["ids"], rtol=RTOL)
+    assert p.ok and p.dist_bit_identical_rows == len(q), p.summary()
