@@ -127,6 +127,12 @@ __device__ __forceinline__ bool elect_one()
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(p));
     return p != 0;
 }
+__device__ __forceinline__ float fmin3(float a, float b, float c)
+{
+    float d;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));     // one FMNMX3
+    return d;
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // per-query epilogue state, owned by one thread for the whole item
@@ -566,16 +572,22 @@ cudaError_t build_tensor_image(hvs_engine *e, int a)
 }
 
 // ---- the sweep --------------------------------------------------------------------------------------
-template <bool PIPE>
+// STATS: the instrumented build (HVS_K3_STATS / HVS_K3_DBG): cycle counters per warp role, hit statistics, the measurement-only
+// modes.  The production instantiation carries none of it (the clock reads alone were ~10 of ~200 instructions per stage).
+#define TICK() (STATS ? clock64() : 0ll)
+template <bool STATS>
 __global__ void __launch_bounds__(NTHR, 1)
 k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slices, const TileItem *__restrict__ items,
               uint32_t n_items, const uint32_t *__restrict__ item_q, const unsigned char *__restrict__ img0,
               const unsigned char *__restrict__ img1, float xnorm_max, float sx, uint64_t *__restrict__ pool,
               uint64_t *__restrict__ cand, uint32_t *__restrict__ cand_cnt, uint32_t *__restrict__ gthr,
               uint32_t *__restrict__ gbest, uint32_t *__restrict__ gcnt, uint32_t *__restrict__ gcut,
-              uint32_t *__restrict__ glock, uint32_t *__restrict__ flags, uint32_t *__restrict__ work_counter, int dbg,
-              uint32_t knobs, unsigned long long *__restrict__ kstat)
+              uint32_t *__restrict__ glock, uint32_t *__restrict__ flags, uint32_t *__restrict__ work_counter, int dbg_arg,
+              uint32_t knobs, unsigned long long *__restrict__ kstat_arg)
 {
+    constexpr bool PIPE = true;                           // the pipelined, unrolled stage scan (the only one kept)
+    const int dbg = STATS ? dbg_arg : 0;
+    unsigned long long *const kstat = STATS ? kstat_arg : nullptr;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TensorSmem &S = *reinterpret_cast<TensorSmem *>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -602,7 +614,7 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
     long long c_mergeonly = 0, c_abuild = 0;
     long long c_wait = 0, c_scan = 0, c_compact = 0, c_merge = 0, c_mma_full = 0, c_mma_tempty = 0, c_items = 0;
     unsigned n_items_done = 0, n_compact = 0, n_surv = 0, n_lhit = 0, n_whit = 0, n_infhit = 0, n_chunks = 0;
-    const long long c_start = clock64();
+    const long long c_start = TICK();
     // running counters: the mbarrier phases continue across items
     uint32_t gt = 0;           // stages issued / consumed so far (producer, MMA)
     uint32_t ga[2] = {0, 0};   // accumulator uses so far, per half (MMA, epilogue)
@@ -618,7 +630,7 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
         const uint32_t row0 = it.row_begin & ~7u;                     // stages start on an 8-row group
         const uint32_t ntiles = (it.row_end - row0 + TN - 1) / TN;
 
-        const long long ta0 = clock64();
+        const long long ta0 = TICK();
         // A operand: fp16(-2 sx q) | 1 1 1 | 0, written straight into the canonical layout.  All MMAs of the
         // previous item have retired (its epilogue consumed every accumulator before the barrier below).
         for (int idx = tid; idx < QT_TENSOR * KU; idx += NTHR) {
@@ -646,7 +658,7 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
         }
         fence_proxy_async();                                          // generic-proxy writes -> visible to the tensor core
         __syncthreads();
-        c_abuild += clock64() - ta0;
+        c_abuild += TICK() - ta0;
         uint32_t item_next = 0;
         if (tid == 0) item_next = atomicAdd(work_counter, 1u);        // everybody has read next_item; the answer is awaited at the end of the item
 
@@ -674,13 +686,13 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
             for (uint32_t t = 0; t < ntiles; ++t) {
                 const uint32_t g = gt + t;
                 const int st = g % NST;
-                { const long long t0 = clock64(); mbar_wait(&S.full[st], (g / NST) & 1); c_mma_full += clock64() - t0; }
+                { const long long t0 = TICK(); mbar_wait(&S.full[st], (g / NST) & 1); c_mma_full += TICK() - t0; }
                 tc_fence_after();
                 if (h < nhalf) {
                     const uint64_t bdesc = smem_desc(smem_u32(S.b[st]));
                     const uint32_t u = ga[h] + t;
                     const int b = u & 1;
-                    { const long long t0 = clock64(); mbar_wait(&S.tempty[h][b], ((u >> 1) & 1) ^ 1); c_mma_tempty += clock64() - t0; }
+                    { const long long t0 = TICK(); mbar_wait(&S.tempty[h][b], ((u >> 1) & 1) ^ 1); c_mma_tempty += TICK() - t0; }
                     tc_fence_after();
                     if (elect_one()) {
                         const uint32_t d = tmem + (uint32_t)(h * 2 + b) * TN;
@@ -725,18 +737,17 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
                 // (a query whose slice starts later in the chunk must not send the warp down the slow path).
                 float thr_s = st.thr;
                 auto scan = [&](const uint32_t (&r)[32], uint32_t rbase) {
-                    float g[4];
+                    float g[4];                                       // four independent chains of 3-input minima (FMNMX3): 18 ops per 32 columns
 #pragma unroll
                     for (int q4 = 0; q4 < 4; ++q4) {
-                        const float a0 = fminf(__uint_as_float(r[8 * q4 + 0]), __uint_as_float(r[8 * q4 + 1]));
-                        const float a1 = fminf(__uint_as_float(r[8 * q4 + 2]), __uint_as_float(r[8 * q4 + 3]));
-                        const float a2 = fminf(__uint_as_float(r[8 * q4 + 4]), __uint_as_float(r[8 * q4 + 5]));
-                        const float a3 = fminf(__uint_as_float(r[8 * q4 + 6]), __uint_as_float(r[8 * q4 + 7]));
-                        g[q4] = fminf(fminf(a0, a1), fminf(a2, a3));
+                        float mm = fmin3(__uint_as_float(r[8 * q4 + 0]), __uint_as_float(r[8 * q4 + 1]), __uint_as_float(r[8 * q4 + 2]));
+                        mm = fmin3(mm, __uint_as_float(r[8 * q4 + 3]), __uint_as_float(r[8 * q4 + 4]));
+                        mm = fmin3(mm, __uint_as_float(r[8 * q4 + 5]), __uint_as_float(r[8 * q4 + 6]));
+                        g[q4] = fminf(mm, __uint_as_float(r[8 * q4 + 7]));
                     }
-                    const bool hit = fminf(fminf(g[0], g[1]), fminf(g[2], g[3])) < thr_s;
+                    const bool hit = fminf(fmin3(g[0], g[1], g[2]), g[3]) < thr_s;
                     const bool whit = __any_sync(FULL, hit);
-                    if (kstat) {                                      // HVS_K3_STATS: how often the element-wise path runs
+                    if (STATS && kstat) {                             // HVS_K3_STATS: how often the element-wise path runs
                         ++n_chunks;
                         n_lhit += hit ? 1u : 0u;
                         n_infhit += (hit && st.thr == __int_as_float(0x7f800000)) ? 1u : 0u;
@@ -772,12 +783,12 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
                     if (own && ep == my_ep) { if (lane == 0) atomicAdd(&S.cepoch[h], 1u); my_ep = ep + 1; }
                     else my_ep = ep;
                     if (own || join) {
-                        const long long t0 = clock64();
-                        n_surv += st.cnt;
+                        const long long t0 = TICK();
+                        if (STATS) n_surv += st.cnt;
                         const uint2 o = compact_warp(st.cnt, st.thr, st.margin, st.qid, qslot < it.nq, pool_warp, gthr, flags, KOUT, part_min, lane);
                         st.cnt = o.x; st.thr = __uint_as_float(o.y);
-                        n_surv -= st.cnt;
-                        c_compact += clock64() - t0; ++n_compact;
+                        if (STATS) { n_surv -= st.cnt; ++n_compact; }
+                        c_compact += TICK() - t0;
                     }
                 };
                 uint32_t gpre = 0xff800000u;                             // okey(+inf)
@@ -787,8 +798,8 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
                     if ((t & 7) == 7) st.thr = fminf(st.thr, okey_inv(gpre));
                     if ((t & 7) == 6 && qslot < it.nq && dbg < 3) gpre = ld_relaxed_u32(&gthr[st.qid]);
                     const int b = u & 1;
-                    { const long long t0 = clock64(); mbar_wait(&S.tfull[h][b], (u >> 1) & 1); c_wait += clock64() - t0; }
-                    const long long ts0 = clock64();
+                    { const long long t0 = TICK(); mbar_wait(&S.tfull[h][b], (u >> 1) & 1); c_wait += TICK() - t0; }
+                    const long long ts0 = TICK();
                     tc_fence_after();
                     const uint32_t tcol = tlane + (uint32_t)(h * 2 + b) * TN;
                     const uint32_t trow0 = row0 + t * TN;
@@ -835,7 +846,7 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&S.tempty[h][b]);
-                    c_scan += clock64() - ts0;
+                    c_scan += TICK() - ts0;
                 }
                 // hand the pools to K5: lists need not be sorted, only short enough
                 if (__any_sync(FULL, st.cnt > (uint32_t)KOUT)) {
@@ -843,11 +854,11 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
                     st.cnt = o.x; st.thr = __uint_as_float(o.y);
                 }
                 // tell the other chunks of these queries what this chunk found (worth it only for long sweeps)
-                const long long tm0 = clock64();
-                n_surv += st.cnt;
+                const long long tm0 = TICK();
+                if (STATS) n_surv += st.cnt;
                 if (ntiles >= 128u && dbg == 0)
                     st.thr = merge_global(st.cnt, st.thr, st.margin, st.qid, qslot < it.nq, pool_warp, gbest, gcnt, gcut, glock, gthr, sparse_sel_ok, lane);
-                c_mergeonly += clock64() - tm0;
+                c_mergeonly += TICK() - tm0;
                 {
                     const uint32_t maxc = __reduce_max_sync(FULL, st.cnt);
                     uint64_t *L = cand + (size_t)(it.out_off + qslot) * KOUT;
@@ -861,21 +872,21 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
                     }
                 }
                 if (qslot < it.nq) cand_cnt[it.out_off + qslot] = st.cnt;
-                c_merge += clock64() - tm0;
+                c_merge += TICK() - tm0;
             }
         }
-        { const long long t0 = clock64();
+        { const long long t0 = TICK();
         gt += ntiles;
         ga[0] += ntiles;
         if (nhalf == 2) ga[1] += ntiles;
         tc_fence_before();
         __syncthreads();                                              // item boundary: A may be rebuilt
         tc_fence_after();
-        c_items += clock64() - t0; }
+        c_items += TICK() - t0; }
         ++n_items_done;
     }
-    if (kstat) {
-        const long long c_total = clock64() - c_start;
+    if (STATS && kstat) {
+        const long long c_total = TICK() - c_start;
         if (warp >= 2 && warp < 10) {
             n_surv = __reduce_add_sync(FULL, n_surv);
             n_lhit = __reduce_add_sync(FULL, n_lhit);
@@ -951,7 +962,6 @@ cudaError_t launch_tile_tensor(hvs_engine *e, const float *queries_dev, const QS
         cudaMemsetAsync(e->d_scratch.p, 0, 256 + 64 * 256, e->stream);
         kstat = e->d_scratch.as<unsigned long long>();
     }
-    static const bool pipe = [] { const char *v = getenv("HVS_K3_PIPE"); return !(v && v[0] == '0'); }();   // default: pipelined, unrolled stage scan
     static const int dbg = [] { const char *v = getenv("HVS_K3_DBG"); return v ? atoi(v) : 0; }();
     static const uint32_t knobs = [] {
         const char *v = getenv("HVS_K3_PARTMIN");
@@ -961,7 +971,7 @@ cudaError_t launch_tile_tensor(hvs_engine *e, const float *queries_dev, const QS
         if (ss && ss[0] == '0') kn |= 0x10000u;
         return kn;
     }();
-    auto kern = pipe ? k_tile_tensor<true> : k_tile_tensor<false>;
+    auto kern = (want_stats || dbg) ? k_tile_tensor<true> : k_tile_tensor<false>;       // instrumented build only on request
     kern<<<grid, NTHR, smem, e->stream>>>(queries_dev, slices_dev, items_dev + item_begin, n_items, item_q_dev,
                                           ix.xb[0].as<unsigned char>(), ix.xb[1].as<unsigned char>(), ix.xnorm_max, ix.img_scale,
                                           e->d_pool.as<uint64_t>() + (size_t)e->pool_slot * e->sm_count * QT_TENSOR * POOL, cand_dev, cand_cnt_dev, gthr_dev, e->d_gbest.as<uint32_t>(),
