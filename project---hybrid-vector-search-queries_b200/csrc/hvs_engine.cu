@@ -616,7 +616,7 @@ extern "C" int hvs_solve_shard_device(hvs_engine *e, const float *queries_dev, u
     ECUDA(launch_plan_search(e, queries_dev, m, d_sl_all));                 // every rank resolves ALL predicates (two binary searches each)
     const uint32_t stripes = shard_stripes(m, world);
     // the assignment runs on the device unless its 64-bit cost arithmetic could overflow (m x n beyond ~10^15) or the host planner is forced
-    const bool on_device = use_device_planner(e) && (double)m * ((double)e->index.n + (double)SHARD_QUERY_COST) * world * stripes < 9.0e18;
+    const bool on_device = use_device_planner(e) && (double)m * ((double)e->index.n + (double)shard_query_cost()) * world * stripes < 9.0e18;
     const uint32_t *own_dev = nullptr;
     uint32_t off = 0, m_own = 0;
     if (on_device) {

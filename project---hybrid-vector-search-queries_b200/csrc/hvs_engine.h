@@ -163,7 +163,8 @@ struct PlanParams {
     bool approx_ok = true;                // false: the index allows no approximate sweep (Index::approx_ok)
 };
 
-constexpr uint64_t SHARD_QUERY_COST = 400000;   // shard_assign: fixed cost of a query, in (query,row) pairs (warm-up + finalize)
+constexpr uint64_t SHARD_QUERY_COST = 400000;   // shard_assign: fixed cost of a query, in (query,row) pairs (warm-up + finalize); HVS_SHARD_QCOST overrides
+uint64_t shard_query_cost();
 constexpr uint32_t SHARD_STRIPES = 16;          // shard_assign: segments per rank
 void shard_assign(const QSlice *slices, uint32_t m, uint32_t world, uint32_t *order, uint32_t *counts);
 void plan_build(const QSlice *slices, uint32_t m, const PlanParams &pp, Plan &out);     // begin + every group + finish

@@ -507,8 +507,16 @@ void plan_finish(const QSlice *sl, uint32_t m, Plan &P)
 // together in runs.  Pure function of the slices: every rank computes the same answer without talking to the others.
 //   order  : all m query indices, rank-major (rank 0's queries first), each rank's in (arena, begin, end) order
 //   counts : queries per rank
+uint64_t shard_query_cost()
+{
+    static const uint64_t v = [] { const char *s = getenv("HVS_SHARD_QCOST"); long long k = s ? atoll(s) : 0; return k > 0 ? (uint64_t)k : SHARD_QUERY_COST; }();
+    return v;
+}
+
 uint32_t shard_stripes(uint32_t m, uint32_t world)
 {
+    static const uint32_t env = [] { const char *s = getenv("HVS_SHARD_STRIPES"); int k = s ? atoi(s) : 0; return (uint32_t)(k > 0 ? k : 0); }();
+    if (env) return env;
     uint32_t stripes = SHARD_STRIPES;
     while (stripes > 1 && (uint64_t)world * stripes * 64 > m) stripes >>= 1;      // small batches: fewer, longer runs
     return stripes;
@@ -523,7 +531,8 @@ void shard_assign(const QSlice *sl, uint32_t m, uint32_t world, uint32_t *order,
     for (uint32_t i = 0; i < m; ++i) keys[sl[i].arena & 1u].push_back({((uint64_t)sl[i].begin << 32) | sl[i].end, i});
     radix_sort_keys(keys[0]);
     radix_sort_keys(keys[1]);
-    auto cost_of = [&](uint32_t i) { return (uint64_t)std::max(sl[i].end - sl[i].begin, (uint32_t)K) + SHARD_QUERY_COST; };
+    const uint64_t qcost = shard_query_cost();
+    auto cost_of = [&](uint32_t i) { return (uint64_t)std::max(sl[i].end - sl[i].begin, (uint32_t)K) + qcost; };
     uint64_t total = 0;
     for (uint32_t i = 0; i < m; ++i) total += cost_of(i);
     const uint64_t nseg = (uint64_t)world * shard_stripes(m, world);

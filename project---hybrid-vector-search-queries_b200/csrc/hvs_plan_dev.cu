@@ -418,7 +418,7 @@ cudaError_t shard_assign_dev(hvs_engine *e, const QSlice *d_sl, uint32_t m, uint
     size_t tb = P.sort_tmp.cap;
     PDCK(cub::DeviceRadixSort::SortPairs(P.sort_tmp.p, tb, P.keys_in.as<uint64_t>(), P.keys.as<uint64_t>(), P.vals_in.as<uint32_t>(),
                                          P.vals.as<uint32_t>(), (int)m, 0, end_bit, s));
-    k_sa_assign<<<1, SCAN_T, 0, s>>>(d_sl, P.vals.as<uint32_t>(), m, world, stripes, SHARD_QUERY_COST, P.sa_owner_in.as<uint32_t>(),
+    k_sa_assign<<<1, SCAN_T, 0, s>>>(d_sl, P.vals.as<uint32_t>(), m, world, stripes, shard_query_cost(), P.sa_owner_in.as<uint32_t>(),
                                      P.sa_counts.as<uint32_t>());
     tb = P.sort_tmp.cap;
     // stable sort by owner: rank-major, each rank's queries keep the (arena, begin, end) order

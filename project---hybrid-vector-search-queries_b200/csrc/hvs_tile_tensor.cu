@@ -60,6 +60,14 @@ constexpr int TN = 128;               // data rows per stage == MMA N
 constexpr int NST = 6;                // B stages in flight
 constexpr int STAGE_B = TN * ROW_B;   // 28,672
 constexpr int A_B = 128 * ROW_B;      // one query half
+#ifndef HVS_K3_ACC64
+#define HVS_K3_ACC64 0                // 1: accumulator hand-off in 64-row halves of a stage (four buffers per query half) instead of 128-row
+                                      // stages (two).  Measured in round 2 (interleaved A/B, headline workload): correct, but the sweep takes
+                                      // 36.7 ms instead of 33.9 -- twice the MMA instructions re-read the A operand twice as often and the
+                                      // barrier traffic doubles, which costs more than the finer hand-off wins.  Kept as a build option.
+#endif
+constexpr int NACC = HVS_K3_ACC64 ? 4 : 2;     // accumulator buffers per query half
+constexpr int ACCN = HVS_K3_ACC64 ? 64 : 128;  // data rows (TMEM columns) per accumulator == MMA N
 constexpr int NTHR = 352;              // warp 0 TMA, warp 1 MMA issuer of query half 0, warps 2..9 epilogue, warp 10 MMA issuer of half 1
 constexpr int POOL = TENSOR_POOL;     // survivor pool entries per query (global memory)
 constexpr uint32_t FULL = 0xffffffffu;
@@ -74,7 +82,7 @@ struct TensorSmem {
     alignas(128) unsigned char b[NST][STAGE_B];
     alignas(128) unsigned char a[2][A_B];
     alignas(8) uint64_t full[NST], empty[NST];
-    alignas(8) uint64_t tfull[2][2], tempty[2][2];
+    alignas(8) uint64_t tfull[2][NACC], tempty[2][NACC];
     uint32_t tmem_base;
     uint32_t next_item;     // dynamic work distribution: the item this CTA sweeps next
     uint32_t cepoch[2];     // per query half: bumped by an epilogue warp that starts a compaction (the others join it)
@@ -107,7 +115,7 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr)
     return d;                                                  // layout_type 0 = SWIZZLE_NONE, base_offset 0
 }
 // c=F32 (bit 4), a=b=F16 (format 0 at bits 7,10), K-major both, N>>3 at bit 17, M>>4 at bit 24
-constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(ACCN >> 3) << 17) | ((128u >> 4) << 24);
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
 {
@@ -597,7 +605,7 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
     if (tid == 0) {
         for (int s = 0; s < NST; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 2); }   // both MMA issuers release a stage
         for (int h = 0; h < 2; ++h)
-            for (int b = 0; b < 2; ++b) { mbar_init(&S.tfull[h][b], 1); mbar_init(&S.tempty[h][b], 4); }
+            for (int b = 0; b < NACC; ++b) { mbar_init(&S.tfull[h][b], 1); mbar_init(&S.tempty[h][b], 4); }
         S.cepoch[0] = 0; S.cepoch[1] = 0;
         S.next_item = atomicAdd(work_counter, 1u);
         mbar_fence_init();
@@ -690,6 +698,27 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
                 tc_fence_after();
                 if (h < nhalf) {
                     const uint64_t bdesc = smem_desc(smem_u32(S.b[st]));
+#if HVS_K3_ACC64
+                    // two 64-row accumulators per stage: the epilogue gets the first half of the stage while the tensor core
+                    // works on the second, and with four buffers per query half a warp that stops for a hit or a compaction
+                    // holds the others up two sub-stages later, not at the next one
+#pragma unroll
+                    for (int sub = 0; sub < 2; ++sub) {
+                        const uint32_t u = 2u * (ga[h] + t) + (uint32_t)sub;
+                        const int b = u & 3;
+                        { const long long t0 = TICK(); mbar_wait(&S.tempty[h][b], ((u >> 2) & 1) ^ 1); c_mma_tempty += TICK() - t0; }
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint32_t d = tmem + (uint32_t)(h * 4 + b) * ACCN;
+                            const uint64_t bsub = bdesc + (uint64_t)(sub * (ACCN / 8) * GROUP_B / 16);   // rows 64.. of the stage: 8 row groups further
+#pragma unroll
+                            for (int j = 0; j < KP / 16; ++j)            // one k-step = two 16-byte units = 256 bytes
+                                tc_mma(d, adesc + (uint64_t)(j * 16), bsub + (uint64_t)(j * 16), IDESC, j > 0);
+                            tc_commit(&S.tfull[h][b]);
+                        }
+                        __syncwarp();
+                    }
+#else
                     const uint32_t u = ga[h] + t;
                     const int b = u & 1;
                     { const long long t0 = TICK(); mbar_wait(&S.tempty[h][b], ((u >> 1) & 1) ^ 1); c_mma_tempty += TICK() - t0; }
@@ -702,6 +731,7 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
                         tc_commit(&S.tfull[h][b]);
                     }
                     __syncwarp();
+#endif
                 }
                 if (elect_one()) tc_commit(&S.empty[st]);               // this half is done with the stage once its MMAs retire
                 __syncwarp();
@@ -797,12 +827,56 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
                     // a look at what other CTAs found out about this query: the load is issued one stage before its use
                     if ((t & 7) == 7) st.thr = fminf(st.thr, okey_inv(gpre));
                     if ((t & 7) == 6 && qslot < it.nq && dbg < 3) gpre = ld_relaxed_u32(&gthr[st.qid]);
+                    const uint32_t trow0 = row0 + t * TN;
+#if HVS_K3_ACC64
+                    {
+                        const uint32_t u0 = 2u * u, u1 = 2u * u + 1u;
+                        const int b0 = u0 & 3, b1 = u1 & 3;
+                        const uint32_t tc0 = tlane + (uint32_t)(h * 4 + b0) * ACCN, tc1 = tlane + (uint32_t)(h * 4 + b1) * ACCN;
+                        make_room(128u);
+                        thr_s = (trow0 < st.qhi && trow0 + TN > st.qlo) ? st.thr : __int_as_float(0xff800000);
+                        { const long long t0 = TICK(); mbar_wait(&S.tfull[h][b0], (u0 >> 2) & 1); c_wait += TICK() - t0; }
+                        const long long ts0 = TICK();
+                        tc_fence_after();
+                        uint32_t ra[32], rb[32];
+                        tmem_ld32(tc0, ra);
+                        tmem_wait_ld();
+                        tmem_ld32(tc0 + 32, rb);
+                        scan(ra, trow0);
+                        tmem_wait_ld();
+                        // the second accumulator is usually complete by now (the tensor core runs ahead): start its first
+                        // load before the last scan of the first; only if it is not, wait for it afterwards
+                        const bool early = __all_sync(FULL, mbar_try_wait(&S.tfull[h][b1], (u1 >> 2) & 1));   // made warp-uniform: "not yet" is always safe
+                        if (early) { tc_fence_after(); tmem_ld32(tc1, ra); }
+                        scan(rb, trow0 + 32);
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&S.tempty[h][b0]);
+                        if (!early) {
+                            const long long t0 = TICK(); mbar_wait(&S.tfull[h][b1], (u1 >> 2) & 1); c_wait += TICK() - t0;
+                            tc_fence_after();
+                            tmem_ld32(tc1, ra);
+                        }
+                        tmem_wait_ld();
+                        tmem_ld32(tc1 + 32, rb);
+                        scan(ra, trow0 + 64);
+                        tmem_wait_ld();
+                        scan(rb, trow0 + 96);
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&S.tempty[h][b1]);
+                        c_scan += TICK() - ts0;
+                    }
+                    if (false) {
+                        const int b = 0; const uint32_t tcol = 0; const long long ts0 = 0;
+#else
                     const int b = u & 1;
                     { const long long t0 = TICK(); mbar_wait(&S.tfull[h][b], (u >> 1) & 1); c_wait += TICK() - t0; }
                     const long long ts0 = TICK();
                     tc_fence_after();
                     const uint32_t tcol = tlane + (uint32_t)(h * 2 + b) * TN;
-                    const uint32_t trow0 = row0 + t * TN;
+                    {
+#endif
                     if (PIPE) {
                         // whole stage unrolled: column offsets are immediates, one room check per stage (128 slots),
                         // the TMEM load of the next 32 columns is in flight while these are scanned
@@ -847,6 +921,7 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&S.tempty[h][b]);
                     c_scan += TICK() - ts0;
+                    }
                 }
                 // hand the pools to K5: lists need not be sorted, only short enough
                 if (__any_sync(FULL, st.cnt > (uint32_t)KOUT)) {
