@@ -163,7 +163,8 @@ struct PlanParams {
     bool approx_ok = true;                // false: the index allows no approximate sweep (Index::approx_ok)
 };
 
-constexpr uint64_t SHARD_QUERY_COST = 400000;   // shard_assign: fixed cost of a query, in (query,row) pairs (warm-up + finalize); HVS_SHARD_QCOST overrides
+constexpr uint64_t SHARD_QUERY_COST = 6000000;  // shard_assign: fixed cost of a query in (query,row) pairs -- threshold warm-up, finalize; measured on 2 GPUs:
+                                                // per-rank solve times 16.9|19.5 ms at 4e5, 17.2|18.7 at 2e6, 18.0|18.4 at 6e6.  HVS_SHARD_QCOST overrides
 uint64_t shard_query_cost();
 constexpr uint32_t SHARD_STRIPES = 16;          // shard_assign: segments per rank
 void shard_assign(const QSlice *slices, uint32_t m, uint32_t world, uint32_t *order, uint32_t *counts);

@@ -601,6 +601,7 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t part_min = knobs & 0xffffu;            // compaction: pool fill from which a lane takes part
     const bool sparse_sel_ok = (knobs & 0x10000u) == 0u;  // merge_global: one-query-at-a-time selection when few lanes need one
+    const bool half_mma = STATS && (knobs & 0x20000u) != 0u;
 
     if (tid == 0) {
         for (int s = 0; s < NST; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 2); }   // both MMA issuers release a stage
@@ -726,8 +727,12 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
                     if (elect_one()) {
                         const uint32_t d = tmem + (uint32_t)(h * 2 + b) * TN;
 #pragma unroll
-                        for (int j = 0; j < KP / 16; ++j)                // one k-step = two 16-byte units = 256 bytes
+                        for (int j = 0; j < KP / 16; ++j) {              // one k-step = two 16-byte units = 256 bytes
+                            // HVS_K3_HALF_MMA=1 (measurement only, results are wrong): 4 of the 7 k-steps -- what a first pass at
+                            // twice the tensor rate (kind::f8f6f4 operands) would cost the tensor pipe
+                            if (half_mma && j >= 4) continue;
                             tc_mma(d, adesc + (uint64_t)(j * 16), bdesc + (uint64_t)(j * 16), IDESC, j > 0);
+                        }
                         tc_commit(&S.tfull[h][b]);
                     }
                     __syncwarp();
@@ -1044,9 +1049,11 @@ cudaError_t launch_tile_tensor(hvs_engine *e, const float *queries_dev, const QS
         uint32_t kn = (uint32_t)(k >= K && k <= POOL - 128 ? k : 256);     // measured: 256 takes the (C,T) head group from 8.9 to 5.8 Mcycles per warp
         const char *ss = getenv("HVS_K3_SPARSE_SEL");
         if (ss && ss[0] == '0') kn |= 0x10000u;
+        const char *hm = getenv("HVS_K3_HALF_MMA");
+        if (hm && hm[0] == '1') kn |= 0x20000u;
         return kn;
     }();
-    auto kern = (want_stats || dbg) ? k_tile_tensor<true> : k_tile_tensor<false>;       // instrumented build only on request
+    auto kern = (want_stats || dbg || (knobs & 0x20000u)) ? k_tile_tensor<true> : k_tile_tensor<false>;       // instrumented build only on request
     kern<<<grid, NTHR, smem, e->stream>>>(queries_dev, slices_dev, items_dev + item_begin, n_items, item_q_dev,
                                           ix.xb[0].as<unsigned char>(), ix.xb[1].as<unsigned char>(), ix.xnorm_max, ix.img_scale,
                                           e->d_pool.as<uint64_t>() + (size_t)e->pool_slot * e->sm_count * QT_TENSOR * POOL, cand_dev, cand_cnt_dev, gthr_dev, e->d_gbest.as<uint32_t>(),

@@ -156,7 +156,7 @@ def _headline_like_slices(m, n, ncat, seed):
 def test_shard_assign_balance_locality_determinism(hvs):
     n, m, ncat = 10_000_000, 40_000, 100
     t, arena, begin, end, cat = _headline_like_slices(m, n, ncat, 7)
-    cost = np.maximum(end - begin, 100).astype(np.int64) + 400_000
+    cost = np.maximum(end - begin, 100).astype(np.int64) + 6_000_000
     for world in (1, 2, 4, 8):
         order, counts = hvs.shard_assign(arena, begin, end, world)
         order2, counts2 = hvs.shard_assign(arena, begin, end, world)
