@@ -257,6 +257,10 @@ static int solve_core_dev(hvs_engine *e, const float *q_dev, uint32_t m, const Q
     cfg.items_per_sm = ips;
     cfg.sm_count = (uint32_t)e->sm_count;
     cfg.kind = tensor ? 1u : 0u;
+    static const uint32_t ct_r = [] { const char *v = getenv("HVS_CT_R"); long k = v ? atol(v) : -1; return (uint32_t)(k >= 0 ? k : 0); }();
+    cfg.ct_min_rows = tensor ? ct_r : 0u;
+    static const uint32_t seed_env = [] { const char *v = getenv("HVS_SEED_PHASE"); return (uint32_t)((v && v[0] == '1') ? 1 : 0); }();
+    cfg.seed_phase = seed_env;
     // A job that cannot reach the tiny-job bound whatever its slices are (m x n pairs at most) needs no plan at all:
     // K4s took the small slices, the CTA scan takes every other query, nothing is read back but the pair count.
     if (small_launched && !cfg.force_tile && (unsigned long long)m * e->index.n < cfg.min_tile_pairs) {
@@ -328,12 +332,19 @@ static int solve_core_dev(hvs_engine *e, const float *q_dev, uint32_t m, const Q
         st.launches += 2;
         e->pool_slot = 0;
         cudaEventRecord(e->evg[0], s);
-        if (tensor)
-            ECUDA(launch_tile_tensor(e, q_dev, d_sl, e->d_items.as<TileItem>(), 0, h.n_items, e->d_item_q.as<uint32_t>(), e->d_cand.as<uint64_t>(),
-                                     e->d_cand_cnt.as<uint32_t>(), e->d_gthr.as<uint32_t>(), e->d_flags.as<uint32_t>()));
-        else
-            ECUDA(launch_tile_ffma(e, q_dev, d_sl, e->d_items.as<TileItem>(), 0, h.n_items, e->d_item_q.as<uint32_t>(), e->d_cand.as<uint64_t>(),
-                                   e->d_cand_cnt.as<uint32_t>(), e->d_gthr.as<uint32_t>(), e->d_flags.as<uint32_t>(), 1.0f));
+        // seed phase (if planned): the items in which slices begin first, everything else in a second launch behind them
+        const uint32_t cut = (h.n_seed_items && h.n_seed_items < h.n_items) ? h.n_seed_items : 0u;
+        for (int ph = 0; ph < 2; ++ph) {
+            const uint32_t ib = ph == 0 ? 0u : cut, ic = ph == 0 ? (cut ? cut : h.n_items) : h.n_items - cut;
+            if (ph == 1 && !cut) break;
+            if (tensor)
+                ECUDA(launch_tile_tensor(e, q_dev, d_sl, e->d_items.as<TileItem>(), ib, ic, e->d_item_q.as<uint32_t>(), e->d_cand.as<uint64_t>(),
+                                         e->d_cand_cnt.as<uint32_t>(), e->d_gthr.as<uint32_t>(), e->d_flags.as<uint32_t>()));
+            else
+                ECUDA(launch_tile_ffma(e, q_dev, d_sl, e->d_items.as<TileItem>(), ib, ic, e->d_item_q.as<uint32_t>(), e->d_cand.as<uint64_t>(),
+                                       e->d_cand_cnt.as<uint32_t>(), e->d_gthr.as<uint32_t>(), e->d_flags.as<uint32_t>(), 1.0f));
+            if (ph == 0 && cut) { cudaEventRecord(e->evg[2], s); st.launches++; }
+        }
         cudaEventRecord(e->evg[1], s);
         st.launches++;
         (tensor ? st.n_items_tensor : st.n_items_ffma) = h.n_items;
@@ -375,9 +386,9 @@ static int solve_core_dev(hvs_engine *e, const float *q_dev, uint32_t m, const Q
     st.ms_solve_device = ev_ms(e->ev[2], e->ev[9]);
     static const bool timeline = getenv("HVS_TIMELINE") != nullptr;
     if (timeline)
-        fprintf(stderr, "timeline(dev planner): plan end %.2f  direct end %.2f  sweep [%.2f, %.2f]  finalize [%.2f, %.2f]  end %.2f  (R=%u, %u items, %u tile queries)\n",
+        fprintf(stderr, "timeline(dev planner): plan end %.2f  direct end %.2f  sweep [%.2f, %.2f]  finalize [%.2f, %.2f]  end %.2f  (R=%u, %u items of which %u seed, %u tile queries)\n",
                 ev_ms(e->ev[2], e->ev[3]), ev_ms(e->ev[2], e->ev[4]), any_items ? ev_ms(e->ev[2], e->evg[0]) : 0.f, any_items ? ev_ms(e->ev[2], e->evg[1]) : 0.f,
-                any_items ? ev_ms(e->ev[2], e->ev[7]) : 0.f, any_items ? ev_ms(e->ev[2], e->ev[8]) : 0.f, st.ms_solve_device, h.R, h.n_items, h.n_tile);
+                any_items ? ev_ms(e->ev[2], e->ev[7]) : 0.f, any_items ? ev_ms(e->ev[2], e->ev[8]) : 0.f, st.ms_solve_device, h.R, h.n_items, h.n_seed_items, h.n_tile);
     return HVS_OK;
 }
 

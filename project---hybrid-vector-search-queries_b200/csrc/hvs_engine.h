@@ -178,14 +178,17 @@ struct PlanCfg {                          // by value to the planner kernels
     uint32_t small_max, min_tile_len;
     uint32_t tile_allowed, force_tile;    // mode != DIRECT && index allows approximate sweeps; mode == TENSOR
     uint32_t bq, items_per_sm, sm_count, kind;
+    uint32_t seed_phase;                  // 1: items that hold queries beginning in their chunk are swept in a first launch
+    uint32_t ct_min_rows;                 // smallest chunk of the (C,T) arena (its slices are short: cutting them finer only repeats threshold warm-ups)
 };
 struct PlanHeader {                       // lives on the device; the host reads it back once per solve (and n_redo at the end)
     unsigned long long pairs, tile_qrows, pairs_tile, pairs_computed, incid;
     uint32_t maxend[2], nchunk[2], chunk_base[2];
-    uint32_t nchunk_total, R, n_tile, n_tile_arena0, n_direct, n_small, n_items, tiny, n_redo, pad[3];
+    uint32_t nchunk_total, R, n_tile, n_tile_arena0, n_direct, n_small, n_items, tiny, n_redo, Ra[2];   // Ra: chunk rows per arena (R = Ra[0])
+    uint32_t n_seed_items;                // items [0, n_seed_items) hold the queries whose slices BEGIN in the item's chunk: swept first (seed phase)
 };
 struct PlanDev {
-    DevBuf header, diff, pref, cls, keys_in, keys, vals_in, vals, nch, qoff, cdiff, cstart, ibase, sort_tmp;
+    DevBuf header, diff, pref, cls, keys_in, keys, vals_in, vals, nch, qoff, cdiff, cbeg, cstart, ibase, ibase_rest, nrest, sort_tmp;
     DevBuf sa_owner_in, sa_owner, sa_order, sa_counts;     // query sharding
     uint32_t nb = 0;
 };

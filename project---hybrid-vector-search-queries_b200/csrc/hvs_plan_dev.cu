@@ -144,10 +144,13 @@ __global__ void k_pd_params(PlanCfg cfg, PlanHeader *__restrict__ H)
         if (R > (1u << 22)) R = 1u << 22;
     }
     H->R = R;
+    H->Ra[0] = R;
+    H->Ra[1] = R < cfg.ct_min_rows ? cfg.ct_min_rows : R;
     uint32_t base = 0;
     // item order: the (C,T) arena's chunks first, then the T arena's
     for (int a = 1; a >= 0; --a) {
-        const uint32_t nc = rows && H->maxend[a] ? (H->maxend[a] + R - 1) / R : 0;
+        const uint32_t Rr = H->Ra[a];
+        const uint32_t nc = rows && H->maxend[a] ? (H->maxend[a] + Rr - 1) / Rr : 0;
         H->nchunk[a] = nc;
         H->chunk_base[a] = base;
         base += nc;
@@ -174,6 +177,7 @@ __global__ void k_pd_keys(const QSlice *__restrict__ sl, uint32_t m, const uint8
 // sorted position t < n_tile  <=>  tile query.
 __global__ void k_pd_chunks(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, uint32_t m, uint32_t nb,
                             const QSlice *__restrict__ sl, PlanHeader *__restrict__ H, int *__restrict__ cdiff,
+                            uint32_t *__restrict__ cbeg /* queries whose slice begins in the chunk */,
                             uint32_t *__restrict__ nch /* [m] chunks of the tile query at sorted position t */)
 {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -182,12 +186,13 @@ __global__ void k_pd_chunks(const uint64_t *__restrict__ keys, const uint32_t *_
     uint32_t n = 0;
     if (c == PD_TILE) {
         const QSlice s = sl[vals[t]];
-        const uint32_t R = H->R, a = s.arena & 1u;
+        const uint32_t a = s.arena & 1u, R = H->Ra[a];
         const uint32_t lo = s.begin / R, hi = (s.end - 1) / R;
         n = hi - lo + 1;
         int *d = cdiff + H->chunk_base[a];
         atomicAdd(&d[lo], 1);
         if (hi + 1 < H->nchunk[a]) atomicAdd(&d[hi + 1], -1);
+        atomicAdd(&cbeg[H->chunk_base[a] + lo], 1u);
         atomicAdd(&H->n_tile, 1u);
         if (a == ARENA_T) atomicAdd(&H->n_tile_arena0, 1u);
     } else if (c == PD_DIRECT) {
@@ -198,15 +203,22 @@ __global__ void k_pd_chunks(const uint64_t *__restrict__ keys, const uint32_t *_
 
 // One CTA: chunk occupancy -> list offsets (cstart) and item offsets per chunk; candidate-list offsets per tile query.
 __global__ void __launch_bounds__(SCAN_T) k_pd_scan(PlanHeader *__restrict__ H, const int *__restrict__ cdiff, uint32_t bq,
+                                                    const uint32_t *__restrict__ cbeg, uint32_t seed_phase,
                                                     uint32_t *__restrict__ cstart /* [nchunk_total+1] */,
-                                                    uint32_t *__restrict__ ibase /* [nchunk_total+1] */,
+                                                    uint32_t *__restrict__ ibase /* [nchunk_total]: first SEED item of the chunk */,
+                                                    uint32_t *__restrict__ ibase_rest /* [nchunk_total]: first other item, relative to the end of the seed items */,
+                                                    uint32_t *__restrict__ nrest /* [nchunk_total]: items of the chunk that hold only queries begun earlier */,
                                                     const uint32_t *__restrict__ nch, uint32_t *__restrict__ qoff /* [n_tile+1] */)
 {
     __shared__ unsigned long long sm64[33];
     __shared__ uint32_t sm32[33];
     // (a) per arena: running occupancy (the difference array restarts at every arena's first chunk)
+    // The chunk's list is in (begin, end) order: the queries that began in an earlier chunk come first.  The items made
+    // only of those ("rest") are swept in the second launch; the items that hold a query BEGINNING in this chunk ("seed":
+    // its threshold starts cold) go first, so that no chunk of a slice is swept before the slice's first chunk has
+    // produced a threshold (seed_phase == 0: every item counts as seed, one launch).
     unsigned long long incid_total = 0;
-    uint32_t items_total = 0;
+    uint32_t seed_total = 0, rest_total = 0;
     for (int pass = 0; pass < 2; ++pass) {
         const int a = pass == 0 ? 1 : 0;                         // same order as chunk_base
         const uint32_t nc = H->nchunk[a], base = H->chunk_base[a];
@@ -215,32 +227,38 @@ __global__ void __launch_bounds__(SCAN_T) k_pd_scan(PlanHeader *__restrict__ H, 
         int s = 0;
         for (uint32_t c = c0; c < c1; ++c) s += cdiff[base + c];
         uint32_t tot32;
-        const uint32_t occ0 = block_excl_scan<uint32_t>((uint32_t)s, &tot32, sm32);   // occupancy just before my first chunk (sums of +-1 stay >= 0 at cell ends)
-        // my chunks' list lengths and item counts
+        const uint32_t occ0 = block_excl_scan<uint32_t>((uint32_t)s, &tot32, sm32);   // occupancy just before my first chunk (mod 2^32 sums of +-1)
         unsigned long long li = 0;
-        uint32_t it = 0, occ = occ0;
-        for (uint32_t c = c0; c < c1; ++c) { occ += (uint32_t)cdiff[base + c]; li += occ; it += (occ + bq - 1) / bq; }
+        uint32_t its = 0, itr = 0, occ = occ0;
+        for (uint32_t c = c0; c < c1; ++c) {
+            occ += (uint32_t)cdiff[base + c];
+            const uint32_t nit = (occ + bq - 1) / bq, nr = seed_phase ? (occ - min(occ, cbeg[base + c])) / bq : 0u;
+            li += occ; its += nit - nr; itr += nr;
+        }
         unsigned long long tot64;
         const unsigned long long lbase = block_excl_scan<unsigned long long>(li, &tot64, sm64) + incid_total;
-        uint32_t itot;
-        const uint32_t ib = block_excl_scan<uint32_t>(it, &itot, sm32) + items_total;
+        uint32_t stot, rtot;
+        const uint32_t sb = block_excl_scan<uint32_t>(its, &stot, sm32) + seed_total;
+        const uint32_t rb = block_excl_scan<uint32_t>(itr, &rtot, sm32) + rest_total;
         unsigned long long l = lbase;
-        uint32_t ii = ib;
+        uint32_t is = sb, ir = rb;
         occ = occ0;
         for (uint32_t c = c0; c < c1; ++c) {
             occ += (uint32_t)cdiff[base + c];
-            cstart[base + c] = (uint32_t)l; ibase[base + c] = ii;
-            l += occ; ii += (occ + bq - 1) / bq;
+            const uint32_t nit = (occ + bq - 1) / bq, nr = seed_phase ? (occ - min(occ, cbeg[base + c])) / bq : 0u;
+            cstart[base + c] = (uint32_t)l; ibase[base + c] = is; ibase_rest[base + c] = ir; nrest[base + c] = nr;
+            l += occ; is += nit - nr; ir += nr;
         }
         incid_total += tot64;
-        items_total += itot;
+        seed_total += stot;
+        rest_total += rtot;
         __syncthreads();
     }
     if (threadIdx.x == 0) {
         cstart[H->nchunk_total] = (uint32_t)incid_total;
-        ibase[H->nchunk_total] = items_total;
         H->incid = incid_total;
-        H->n_items = items_total;
+        H->n_items = seed_total + rest_total;
+        H->n_seed_items = seed_total;
     }
     // (b) candidate-list offsets of the tile queries (sorted positions 0..n_tile)
     const uint32_t nt = H->n_tile;
@@ -260,6 +278,7 @@ __global__ void __launch_bounds__(SCAN_T) k_pd_scan(PlanHeader *__restrict__ H, 
 __global__ void __launch_bounds__(256) k_pd_fill(const PlanHeader *__restrict__ H, const uint32_t *__restrict__ vals,
                                                  const QSlice *__restrict__ sl, uint32_t bq, uint32_t kind,
                                                  const uint32_t *__restrict__ cstart, const uint32_t *__restrict__ ibase,
+                                                 const uint32_t *__restrict__ ibase_rest, const uint32_t *__restrict__ nrest,
                                                  const uint32_t *__restrict__ qoff, uint32_t *__restrict__ item_q,
                                                  TileItem *__restrict__ items, uint32_t *__restrict__ qlists,
                                                  unsigned long long *__restrict__ pairs_computed)
@@ -270,7 +289,7 @@ __global__ void __launch_bounds__(256) k_pd_fill(const PlanHeader *__restrict__ 
     if (gc >= H->nchunk_total) return;
     const uint32_t a = gc >= H->chunk_base[0] && H->nchunk[0] && gc < H->chunk_base[0] + H->nchunk[0] ? 0u : 1u;
     const uint32_t c = gc - H->chunk_base[a];
-    const uint32_t R = H->R;
+    const uint32_t R = H->Ra[a];
     const uint64_t r0 = (uint64_t)c * R, r1 = r0 + R;
     // sorted tile queries of this arena: arena 0 occupies sorted positions [0, n0), arena 1 [n0, n_tile)
     const uint32_t n0 = H->n_tile_arena0, nt = H->n_tile;
@@ -325,7 +344,9 @@ __global__ void __launch_bounds__(256) k_pd_fill(const PlanHeader *__restrict__ 
         if (lane == 0) {
             TileItem it;
             it.arena = a; it.row_begin = lo; it.row_end = hi; it.nq = nq; it.q_off = q0; it.out_off = q0; it.kind = kind; it.pad = 0;
-            items[ibase[gc] + j] = it;
+            // the first nrest items of the list hold only queries begun in earlier chunks: second launch, behind all seed items
+            const uint32_t nr = nrest[gc];
+            items[j < nr ? H->n_seed_items + ibase_rest[gc] + j : ibase[gc] + (j - nr)] = it;
             atomicAdd(pairs_computed, (unsigned long long)(hi - lo) * nq);
         }
     }
@@ -439,7 +460,7 @@ cudaError_t plan_dev_begin(hvs_engine *e, const QSlice *d_sl, uint32_t m, const 
     uint32_t nb = 1;
     while ((1ull << nb) <= (uint64_t)n) ++nb;                   // begin < 2^nb, end <= n < 2^nb  (end field has nb + 1 bits)
     P.nb = nb;
-    const uint32_t max_chunks = 2 * (n / 8192 + 2);
+    const uint32_t max_chunks = 2 * (n / 8192 + 2);          // R >= 8192 in both arenas
     PDCK(P.header.ensure(sizeof(PlanHeader)));
     PDCK(P.diff.ensure((size_t)2 * ncell * 4));
     PDCK(P.pref.ensure((size_t)2 * (ncell + 1) * 8));
@@ -451,6 +472,9 @@ cudaError_t plan_dev_begin(hvs_engine *e, const QSlice *d_sl, uint32_t m, const 
     PDCK(P.nch.ensure((size_t)m * 4));
     PDCK(P.qoff.ensure((size_t)(m + 1) * 4));
     PDCK(P.cdiff.ensure((size_t)(max_chunks + 2) * 4));
+    PDCK(P.cbeg.ensure((size_t)(max_chunks + 2) * 4));
+    PDCK(P.ibase_rest.ensure((size_t)(max_chunks + 2) * 4));
+    PDCK(P.nrest.ensure((size_t)(max_chunks + 2) * 4));
     PDCK(P.cstart.ensure((size_t)(max_chunks + 2) * 4));
     PDCK(P.ibase.ensure((size_t)(max_chunks + 2) * 4));
     PDCK(e->h_header.ensure(sizeof(PlanHeader)));
@@ -458,6 +482,7 @@ cudaError_t plan_dev_begin(hvs_engine *e, const QSlice *d_sl, uint32_t m, const 
     PDCK(cudaMemsetAsync(H, 0, sizeof(PlanHeader), s));
     PDCK(cudaMemsetAsync(P.diff.p, 0, (size_t)2 * ncell * 4, s));
     PDCK(cudaMemsetAsync(P.cdiff.p, 0, (size_t)(max_chunks + 2) * 4, s));
+    PDCK(cudaMemsetAsync(P.cbeg.p, 0, (size_t)(max_chunks + 2) * 4, s));
     int *diff0 = P.diff.as<int>(), *diff1 = diff0 + ncell;
     long long *pref0 = P.pref.as<long long>(), *pref1 = pref0 + ncell + 1;
     const unsigned gb = (m + 255) / 256;
@@ -476,9 +501,10 @@ cudaError_t plan_dev_begin(hvs_engine *e, const QSlice *d_sl, uint32_t m, const 
     tb = P.sort_tmp.cap;
     PDCK(cub::DeviceRadixSort::SortPairs(P.sort_tmp.p, tb, P.keys_in.as<uint64_t>(), P.keys.as<uint64_t>(), P.vals_in.as<uint32_t>(),
                                          P.vals.as<uint32_t>(), (int)m, 0, end_bit, s));
-    k_pd_chunks<<<gb, 256, 0, s>>>(P.keys.as<uint64_t>(), P.vals.as<uint32_t>(), m, nb, d_sl, H, P.cdiff.as<int>(), P.nch.as<uint32_t>());
-    k_pd_scan<<<1, SCAN_T, 0, s>>>(H, P.cdiff.as<int>(), cfg.bq, P.cstart.as<uint32_t>(), P.ibase.as<uint32_t>(), P.nch.as<uint32_t>(),
-                                   P.qoff.as<uint32_t>());
+    k_pd_chunks<<<gb, 256, 0, s>>>(P.keys.as<uint64_t>(), P.vals.as<uint32_t>(), m, nb, d_sl, H, P.cdiff.as<int>(), P.cbeg.as<uint32_t>(),
+                                   P.nch.as<uint32_t>());
+    k_pd_scan<<<1, SCAN_T, 0, s>>>(H, P.cdiff.as<int>(), cfg.bq, P.cbeg.as<uint32_t>(), cfg.seed_phase, P.cstart.as<uint32_t>(), P.ibase.as<uint32_t>(),
+                                   P.ibase_rest.as<uint32_t>(), P.nrest.as<uint32_t>(), P.nch.as<uint32_t>(), P.qoff.as<uint32_t>());
     PDCK(cudaGetLastError());
     PDCK(cudaMemcpyAsync(e->h_header.p, H, sizeof(PlanHeader), cudaMemcpyDeviceToHost, s));
     PDCK(cudaStreamSynchronize(s));
@@ -492,7 +518,7 @@ cudaError_t plan_dev_fill(hvs_engine *e, const QSlice *d_sl, const PlanHeader &h
     if (!h.nchunk_total) return cudaSuccess;
     PlanDev &P = e->pdev;
     k_pd_fill<<<h.nchunk_total, 256, 0, e->stream>>>(P.header.as<PlanHeader>(), P.vals.as<uint32_t>(), d_sl, cfg.bq, cfg.kind, P.cstart.as<uint32_t>(),
-                                                      P.ibase.as<uint32_t>(), P.qoff.as<uint32_t>(), item_q_dev, items_dev, qlists_dev,
+                                                      P.ibase.as<uint32_t>(), P.ibase_rest.as<uint32_t>(), P.nrest.as<uint32_t>(), P.qoff.as<uint32_t>(), item_q_dev, items_dev, qlists_dev,
                                                       &P.header.as<PlanHeader>()->pairs_computed);
     return cudaGetLastError();
 }

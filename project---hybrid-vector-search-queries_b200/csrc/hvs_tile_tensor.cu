@@ -812,11 +812,18 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
                 auto make_room = [&](uint32_t slack) {
                     if (dbg >= 3) { if (st.cnt > (uint32_t)POOL - slack) st.cnt = 0; return; }   // measurement only
                     const uint32_t ep = *reinterpret_cast<volatile uint32_t *>(&S.cepoch[h]);
-                    const bool own = __any_sync(FULL, st.cnt > (uint32_t)POOL - slack ||
-                                                          (st.cnt >= 192u && st.thr == __int_as_float(0x7f800000)));
-                    const bool join = ep != my_ep && __any_sync(FULL, st.cnt >= max(160u, part_min));
-                    if (own && ep == my_ep) { if (lane == 0) atomicAdd(&S.cepoch[h], 1u); my_ep = ep + 1; }
-                    else my_ep = ep;
+                    const bool full = st.cnt > (uint32_t)POOL - slack || (st.cnt >= 192u && st.thr == __int_as_float(0x7f800000));
+                    bool own, join = false;
+                    if (ep == my_ep) {                                // the common case costs one vote
+                        own = __any_sync(FULL, full);
+                        if (!own) return;
+                        if (lane == 0) atomicAdd(&S.cepoch[h], 1u);
+                        my_ep = ep + 1;
+                    } else {                                          // another warp of this half started a compaction: join if worthwhile
+                        own = __any_sync(FULL, full);
+                        join = __any_sync(FULL, st.cnt >= max(160u, part_min));
+                        my_ep = ep;
+                    }
                     if (own || join) {
                         const long long t0 = TICK();
                         if (STATS) n_surv += st.cnt;

@@ -87,6 +87,7 @@ def solve_sharded(engine, queries_dev, rank: int, world: int, scratch=None):
     every rank solves its share (hvs_solve_shard_device) and ONE all_gather_into_tensor brings the rows together;
     returns the [m, 100] int32 ids in query order, on every rank.  `scratch` (a dict, optional) keeps the device
     buffers between calls."""
+    import numpy as np
     import torch
     import torch.distributed as td
     m = queries_dev.shape[0]
@@ -100,15 +101,22 @@ def solve_sharded(engine, queries_dev, rank: int, world: int, scratch=None):
     if world == 1:
         sc["out"].index_copy_(0, torch.from_numpy(order.astype("int64")).to(dev), sc["own"])
         return sc["out"]
-    src, dst, longest = scatter_index(order, counts)
+    longest = int(counts.max())
     if sc.get("cap", -1) < longest:                        # rows every rank contributes to the gather (same on all ranks)
         sc["cap"] = min(m, longest + longest // 8 + 8)
         sc["gath"] = torch.empty((world * sc["cap"], 100), dtype=torch.int32, device=dev)
+        sc.pop("order", None)
     cap = sc["cap"]
-    if cap != longest and longest:                         # the gather block is sized with slack: re-derive the row positions
-        src = (src // longest) * cap + (src % longest)
+    prev = sc.get("order")
+    if prev is None or not (np.array_equal(prev[0], order) and np.array_equal(prev[1], counts)):
+        # where row j of the padded [world, cap, 100] gather goes; kept while the assignment stays the same (a server that
+        # answers the same filter mix again, the timed loop of bench.py): two small H2D copies saved per call
+        src, dst, _ = scatter_index(order, counts)
+        if cap != longest and longest:                     # the gather block is sized with slack: re-derive the row positions
+            src = (src // longest) * cap + (src % longest)
+        sc["order"] = (order.copy(), counts.copy())
+        sc["idx"] = torch.from_numpy(src).to(dev, non_blocking=True)
+        sc["to"] = torch.from_numpy(dst).to(dev, non_blocking=True)
     td.all_gather_into_tensor(sc["gath"], sc["own"][:cap])
-    idx = torch.from_numpy(src).to(dev, non_blocking=True)
-    to = torch.from_numpy(dst).to(dev, non_blocking=True)
-    sc["out"].index_copy_(0, to, sc["gath"].index_select(0, idx))
+    sc["out"].index_copy_(0, sc["to"], sc["gath"].index_select(0, sc["idx"]))
     return sc["out"]

@@ -1,4 +1,4 @@
-"""Build profiles/r1_traffic.json from ncu CSVs (--metrics dram__bytes_read.sum,dram__bytes_write.sum) of
+"""Build profiles/traffic.json (round 1: r1_traffic.json) from ncu CSVs (--metrics dram__bytes_read.sum,dram__bytes_write.sum) of
 `python bench.py ... --steps 1 --warmup 1`: per workload and kernel, DRAM bytes per solve (= per bench step): the sum
 over all launches of the capture divided by the number of solves in it (every solve launches k_plan_search once).
 usage: python tools/traffic_json.py out.json workload=csv:"command" [workload=csv:"command" ...]"""
@@ -6,7 +6,7 @@ import csv, io, json, sys
 from collections import defaultdict
 
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
-KERNELS = ("k_tile_tensor", "k_tile_ffma", "k_direct", "k_finalize", "k_plan_search")
+KERNELS = ("k_tile_tensor", "k_tile_ffma", "k_direct", "k_small", "k_finalize", "k_plan_search")
 out = {}
 for spec in sys.argv[2:]:
     wl, rest = spec.split("=", 1)
