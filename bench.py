@@ -44,6 +44,9 @@ WORKLOADS = {
     "large": (10_000_000, 40_000, 100, (0, 1, 2, 3), None),          # configs[2]  <- the metric's config
     "type0": (10_000_000, 40_000, 100, (0,), None),                  # configs[3]
     "selective": (10_000_000, 40_000, 1000, (3,), 0.06),             # configs[4]
+    # diagnostics (not BASELINE configs): one query type at a time on the headline data
+    "type2": (10_000_000, 40_000, 100, (2,), None),
+    "type13": (10_000_000, 40_000, 100, (1, 3), None),
 }
 DATA_SEED, QUERY_SEED, RECAT_SEED = 3, 4, 5
 

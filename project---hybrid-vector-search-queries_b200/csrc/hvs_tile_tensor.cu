@@ -1041,7 +1041,7 @@ cudaError_t launch_tile_tensor(hvs_engine *e, const float *queries_dev, const QS
     const uint32_t grid = n_items < (uint32_t)e->sm_count ? n_items : (uint32_t)e->sm_count;
     cudaError_t c = cudaSuccess;
     if (e->work_slot >= 63) return cudaErrorInvalidValue;
-    static const bool want_stats = getenv("HVS_K3_STATS") != nullptr;
+    static const bool want_stats = [] { const char *v = getenv("HVS_K3_STATS"); return v && v[0] != 0 && v[0] != '0'; }();
     unsigned long long *kstat = nullptr;
     if (want_stats) {
         c = e->d_scratch.ensure(256 + 64 * 256);
