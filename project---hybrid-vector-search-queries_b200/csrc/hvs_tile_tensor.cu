@@ -224,7 +224,7 @@ __device__ __noinline__ uint2 compact_warp(uint32_t cnt, float thr, float margin
                     ++pos;
                 }
             if (w > keep_cap) {                                       // more rows inside the margin than a list may hold
-                if (flags && lane == 0) flags[q_src] = 1u;
+                if (lane == 0) flags[q_src] = 1u;
                 w = keep_cap;
             }
             const float mine = nextafterf(lim, __int_as_float(0x7f800000));
@@ -602,6 +602,7 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
     const uint32_t part_min = knobs & 0xffffu;            // compaction: pool fill from which a lane takes part
     const bool sparse_sel_ok = (knobs & 0x10000u) == 0u;  // merge_global: one-query-at-a-time selection when few lanes need one
     const bool half_mma = STATS && (knobs & 0x20000u) != 0u;
+    const bool l2_hints = (knobs & 0x40000u) != 0u;       // image stages evict_last, candidate lists evict_first
 
     if (tid == 0) {
         for (int s = 0; s < NST; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 2); }   // both MMA issuers release a stage
@@ -674,13 +675,15 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
         if (warp == 0) {
             // ===== TMA producer (whole warp runs the loop, one elected lane talks to the TMA engine) =====
             const unsigned char *src = img + (size_t)(row0 >> 3) * GROUP_B;
+            const uint64_t pol = l2_policy_evict_last();             // the other CTAs sweeping this chunk read the same stages shortly after
             for (uint32_t t = 0; t < ntiles; ++t) {
                 const uint32_t g = gt + t;
                 const int st = g % NST;
                 mbar_wait(&S.empty[st], ((g / NST) & 1) ^ 1);
                 if (elect_one()) {
                     mbar_expect_tx(&S.full[st], STAGE_B);
-                    bulk_g2s(S.b[st], src + (size_t)t * STAGE_B, STAGE_B, &S.full[st]);
+                    if (l2_hints) bulk_g2s_hint(S.b[st], src + (size_t)t * STAGE_B, STAGE_B, &S.full[st], pol);
+                    else bulk_g2s(S.b[st], src + (size_t)t * STAGE_B, STAGE_B, &S.full[st]);
                 }
                 __syncwarp();
             }
@@ -949,13 +952,14 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
                 {
                     const uint32_t maxc = __reduce_max_sync(FULL, st.cnt);
                     uint64_t *L = cand + (size_t)(it.out_off + qslot) * KOUT;
+                    const uint64_t polw = l2_policy_evict_first();    // written once, read by K5 after the whole sweep: do not displace the image
                     for (uint32_t i0 = 0; i0 < maxc; i0 += 16) {      // batches of 16 loads in flight
                         uint64_t e[16];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) e[j] = __ldcg(mypool + (size_t)32 * (i0 + j));
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
-                            if (i0 + j < st.cnt) L[i0 + j] = e[j];
+                            if (i0 + j < st.cnt) { if (l2_hints) st_u64_hint(L + i0 + j, e[j], polw); else L[i0 + j] = e[j]; }
                     }
                 }
                 if (qslot < it.nq) cand_cnt[it.out_off + qslot] = st.cnt;
@@ -1056,6 +1060,8 @@ cudaError_t launch_tile_tensor(hvs_engine *e, const float *queries_dev, const QS
         uint32_t kn = (uint32_t)(k >= K && k <= POOL - 128 ? k : 256);     // measured: 256 takes the (C,T) head group from 8.9 to 5.8 Mcycles per warp
         const char *ss = getenv("HVS_K3_SPARSE_SEL");
         if (ss && ss[0] == '0') kn |= 0x10000u;
+        const char *lh = getenv("HVS_K3_L2HINTS");
+        if (lh && lh[0] == '1') kn |= 0x40000u;
         const char *hm = getenv("HVS_K3_HALF_MMA");
         if (hm && hm[0] == '1') kn |= 0x20000u;
         return kn;

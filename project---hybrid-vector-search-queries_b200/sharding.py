@@ -16,13 +16,6 @@ Works with the nccl backend (GPU tensors) and with gloo (CPU tensors; used by th
 from __future__ import annotations
 
 
-def query_shard(m: int, rank: int, world: int) -> tuple[int, int]:
-    """Contiguous, balanced split of m queries: ranks < m % world get one more."""
-    base, rem = divmod(m, world)
-    lo = rank * base + min(rank, rem)
-    return lo, lo + base + (1 if rank < rem else 0)
-
-
 def data_shard(n: int, rank: int, world: int) -> tuple[int, int]:
     """Rows [lo, hi) of D that rank `rank` indexes (same arithmetic on every rank)."""
     return rank * n // world, (rank + 1) * n // world
@@ -49,27 +42,6 @@ def gather_partials(dist, ids, cnt, world: int, out=None):
     td.all_gather_into_tensor(g_cnt, cnt.contiguous())
     return (g_dist.view((world, m) + tuple(dist.shape[1:])), g_ids.view((world, m) + tuple(ids.shape[1:])),
             g_cnt.view(world, m))
-
-
-def gather_query_results(ids_local, m: int, world: int):
-    """Query-sharded runs that want the whole result on every rank (not on the timed path):
-    all-gather variable-length row blocks by padding to the largest shard."""
-    import torch
-    import torch.distributed as td
-    rank = td.get_rank()
-    width = ids_local.shape[1]
-    longest = max(query_shard(m, r, world)[1] - query_shard(m, r, world)[0] for r in range(world))
-    pad = torch.zeros((longest, width), dtype=ids_local.dtype, device=ids_local.device)
-    pad[: ids_local.shape[0]] = ids_local
-    out = torch.empty((world * longest, width), dtype=ids_local.dtype, device=ids_local.device)
-    td.all_gather_into_tensor(out, pad)
-    out = out.view(world, longest, width)
-    parts = []
-    for r in range(world):
-        lo, hi = query_shard(m, r, world)
-        parts.append(out[r, : hi - lo])
-    del rank
-    return torch.cat(parts, 0)
 
 
 def scatter_index(order, counts):

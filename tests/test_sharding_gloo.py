@@ -58,12 +58,8 @@ def _worker(rank, world, port, n, m, out_dir):
     dist, ids, cnt = _partial_from_oracle(O, d[lo:hi], lo, q, n)
     g_dist, g_ids, g_cnt = sh.gather_partials(torch.from_numpy(dist), torch.from_numpy(ids.view(np.int32)),
                                               torch.from_numpy(cnt.view(np.int32)), world)
-    # query-sharded result exchange
-    qlo, qhi = sh.query_shard(m, rank, world)
-    mine = torch.arange(qlo, qhi, dtype=torch.int32).unsqueeze(1).repeat(1, 3)
-    allq = sh.gather_query_results(mine, m, world)
     np.savez(os.path.join(out_dir, f"r{rank}.npz"), g_dist=g_dist.numpy(), g_ids=g_ids.numpy().view(np.uint32),
-             g_cnt=g_cnt.numpy().view(np.uint32), allq=allq.numpy())
+             g_cnt=g_cnt.numpy().view(np.uint32))
     td.destroy_process_group()
 
 
@@ -91,13 +87,6 @@ def _merge_numpy(O, d, q, g_dist, g_ids, g_cnt):
 
 def test_shard_arithmetic(hvs):
     sh = importlib.import_module(PKG + ".sharding")
-    for m, w in [(10, 3), (40000, 8), (7, 8), (0, 2)]:
-        cover = []
-        for r in range(w):
-            lo, hi = sh.query_shard(m, r, w)
-            assert 0 <= lo <= hi <= m and hi - lo in (m // w, m // w + 1)
-            cover += list(range(lo, hi))
-        assert cover == list(range(m))
     for n, w in [(10_000_000, 8), (1001, 2), (100, 3)]:
         edges = [sh.data_shard(n, r, w) for r in range(w)]
         assert edges[0][0] == 0 and edges[-1][1] == n
@@ -116,7 +105,7 @@ def test_data_sharded_gather_and_merge_world2(tmp_path, oracle, check):
     ref, nmatch = oracle.vec_query(d, q, want_dist=False, want_nmatch=True)
     assert (nmatch < K).any() and (nmatch >= K).any()          # both the pad rule and the plain merge are exercised
     r0, r1 = np.load(tmp_path / "r0.npz"), np.load(tmp_path / "r1.npz")
-    for k in ("g_dist", "g_ids", "g_cnt", "allq"):                 # every rank holds the same gathered tensors
+    for k in ("g_dist", "g_ids", "g_cnt"):                         # every rank holds the same gathered tensors
         assert np.array_equal(r0[k], r1[k]), k
     assert r0["g_dist"].shape == (world, m, K) and r0["g_cnt"].shape == (world, m)
     assert np.array_equal(r0["g_cnt"].astype(np.int64).sum(0), nmatch)
@@ -126,7 +115,6 @@ def test_data_sharded_gather_and_merge_world2(tmp_path, oracle, check):
     got = _merge_numpy(oracle, d, q, r0["g_dist"], r0["g_ids"], r0["g_cnt"])
     p = check.compare(d, q, ref, got)
     assert p.ok and p.dist_bit_identical_rows == m, p.summary()
-    assert np.array_equal(r0["allq"][:, 0], np.arange(m))          # query-sharded blocks come back in query order
 
 
 # ---- query-sharded solve of ONE batch (strong scaling): assignment + the single all-gather ---------------------------
