@@ -87,7 +87,10 @@ struct Index {
 constexpr int QT = 128;          // queries per FFMA tile item (K2)
 constexpr int QT_TENSOR = 256;   // queries per tensor tile item (K3): two M=128 halves share every data stage
 constexpr int KOUT = 256;        // candidates an item hands to finalize per query (<= this many)
-constexpr int TENSOR_POOL = 512; // K3: survivor pool entries per (CTA, query) in global memory
+#ifndef HVS_POOL
+#define HVS_POOL 512
+#endif
+constexpr int TENSOR_POOL = HVS_POOL; // K3: survivor pool entries per (CTA, query) in global memory
 constexpr int TENSOR_GBEST = 128;
 constexpr uint32_t SMALL_MAX = 255;  // K4s: slices of at most this many rows get a warp each (8 rounds of 32 rows; must stay below PlanParams::min_tile_len:
                                      // never tile queries).  Longer sparse slices take the CTA-per-query scan, which has the lower latency per query.

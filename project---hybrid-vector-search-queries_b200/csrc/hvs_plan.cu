@@ -42,14 +42,18 @@ __global__ void k_plan_search(const float *__restrict__ queries, uint32_t m, con
                               const uint64_t *__restrict__ keys_ct, uint32_t n, uint32_t small_max, QSlice *__restrict__ out,
                               unsigned long long *__restrict__ k1acc /* {sum of max(len, K), queries with len <= small_max} */)
 {
+    __shared__ unsigned long long s_pairs;
+    __shared__ unsigned int s_small;
+    if (threadIdx.x == 0) { s_pairs = 0; s_small = 0; }
+    __syncthreads();
     uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (q >= m) return;
+    if (q < m) {                                  // (whole warps: one query per warp)
     const float *row = queries + (size_t)q * QROW;
     float acc = 0.f;
     for (int i = lane; i < DIM; i += 32) { float v = row[4 + i]; acc = fmaf(v, v, acc); }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane != 0) return;
+    if (lane == 0) {
     uint32_t type = f2u32_x86(row[0]);           // baseline.hpp:90
     int32_t v = f2i32_x86(row[1]);               // baseline.hpp:91 (truncation toward zero)
     float l = row[2], r = row[3];                // baseline.hpp:92-93
@@ -77,8 +81,15 @@ __global__ void k_plan_search(const float *__restrict__ queries, uint32_t m, con
     if (s.end < s.begin) s.end = s.begin;         // l > r
     out[q] = s;
     const uint32_t len = s.end - s.begin;
-    atomicAdd(&k1acc[0], (unsigned long long)(len > (uint32_t)K ? len : (uint32_t)K));
-    if (len <= small_max) atomicAdd(&k1acc[1], 1ull);
+    atomicAdd(&s_pairs, (unsigned long long)(len > (uint32_t)K ? len : (uint32_t)K));     // per block first: one global atomic pair per 8 queries
+    if (len <= small_max) atomicAdd(&s_small, 1u);
+    }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        atomicAdd(&k1acc[0], s_pairs);
+        if (s_small) atomicAdd(&k1acc[1], (unsigned long long)s_small);
+    }
 }
 
 cudaError_t launch_plan_search(hvs_engine *e, const float *queries_dev, uint32_t m, QSlice *slices_dev)

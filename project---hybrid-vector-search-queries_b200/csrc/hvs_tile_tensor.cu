@@ -76,7 +76,8 @@ constexpr int SPARSE_LANES = 6;
 constexpr int SPARSE_SEL = 8;         // merge_global: up to this many lanes whose global list needs a new K-th best are handled one query at a time       // compaction: up to this many participating lanes are handled one query at a time by the whole warp
 
 static_assert(QT_TENSOR == 256, "two M=128 halves");
-static_assert(POOL == 512 && KOUT <= POOL - 32, "pool must take 32 more survivors after a compaction");
+static_assert(POOL % 64 == 0 && POOL >= 512 && POOL <= 1024 && KOUT <= POOL - 32, "pool must take 32 more survivors after a compaction; passes read it in batches of 64");
+constexpr int PPL = POOL / 32;        // pool entries per lane when a whole warp holds ONE query's pool in registers
 
 struct TensorSmem {
     alignas(128) unsigned char b[NST][STAGE_B];
@@ -174,22 +175,21 @@ __device__ __noinline__ uint2 compact_warp(uint32_t cnt, float thr, float margin
     // rank is bracketed with warp-wide counts -- no further memory passes -- and the kept entries are written back.
     const uint32_t pmask = __ballot_sync(FULL, part);
     if (__popc(pmask) <= SPARSE_LANES) {
-        static_assert(POOL == 512, "16 entries per lane");
         uint32_t my_cnt = cnt;
         float my_thr = thr;
         for (uint32_t mm = pmask; mm; mm &= mm - 1u) {
             const int src = __ffs((int)mm) - 1;
             const uint32_t c = __shfl_sync(FULL, cnt, src), q_src = __shfl_sync(FULL, qid, src);
             const float thr_src = __shfl_sync(FULL, thr, src), margin_src = __shfl_sync(FULL, margin, src);
-            uint64_t e[16];
+            uint64_t e[PPL];
             uint32_t klo = 0xffffffffu, khi = 0u;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
+            for (int j = 0; j < PPL; ++j) {
                 const uint32_t idx = (uint32_t)lane + 32u * j;
                 e[j] = idx < c ? __ldcg(pool_warp + (size_t)32 * idx + src) : ~0ull;
             }
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
+            for (int j = 0; j < PPL; ++j)
                 if ((uint32_t)lane + 32u * j < c) { klo = min(klo, (uint32_t)(e[j] >> 32)); khi = max(khi, (uint32_t)(e[j] >> 32)); }
             klo = __reduce_min_sync(FULL, klo);
             khi = __reduce_max_sync(FULL, khi);
@@ -200,7 +200,7 @@ __device__ __noinline__ uint2 compact_warp(uint32_t cnt, float thr, float margin
                     const uint32_t mid = select_probe(klo, khi, clo, chi, it);
                     uint32_t n = 0;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) n += ((uint32_t)lane + 32u * j < c && (uint32_t)(e[j] >> 32) <= mid) ? 1u : 0u;
+                    for (int j = 0; j < PPL; ++j) n += ((uint32_t)lane + 32u * j < c && (uint32_t)(e[j] >> 32) <= mid) ? 1u : 0u;
                     n = __reduce_add_sync(FULL, n);
                     if (n >= (uint32_t)K) { khi = mid; chi = n; if (n <= (uint32_t)K + 8u) break; }
                     else { klo = mid; clo = n; }
@@ -210,7 +210,7 @@ __device__ __noinline__ uint2 compact_warp(uint32_t cnt, float thr, float margin
             const uint32_t limk = okey(lim);
             uint32_t kc = 0;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) kc += ((uint32_t)lane + 32u * j < c && (uint32_t)(e[j] >> 32) <= limk) ? 1u : 0u;
+            for (int j = 0; j < PPL; ++j) kc += ((uint32_t)lane + 32u * j < c && (uint32_t)(e[j] >> 32) <= limk) ? 1u : 0u;
             uint32_t pos = kc;                                        // inclusive scan over the lanes
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL, pos, o); if (lane >= o) pos += v; }
@@ -218,7 +218,7 @@ __device__ __noinline__ uint2 compact_warp(uint32_t cnt, float thr, float margin
             pos -= kc;
             __syncwarp();                                             // every lane holds its share: the pool may be rewritten
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
+            for (int j = 0; j < PPL; ++j)
                 if ((uint32_t)lane + 32u * j < c && (uint32_t)(e[j] >> 32) <= limk) {
                     if (pos < keep_cap) pool_warp[(size_t)32 * pos + src] = e[j];
                     ++pos;
@@ -603,6 +603,7 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
     const bool sparse_sel_ok = (knobs & 0x10000u) == 0u;  // merge_global: one-query-at-a-time selection when few lanes need one
     const bool half_mma = STATS && (knobs & 0x20000u) != 0u;
     const bool l2_hints = (knobs & 0x40000u) != 0u;       // image stages evict_last, candidate lists evict_first
+    const uint32_t trig = (knobs >> 20) & 0x3ffu;         // pool fill that starts a compaction
 
     if (tid == 0) {
         for (int s = 0; s < NST; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 2); }   // both MMA issuers release a stage
@@ -815,7 +816,11 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
                 auto make_room = [&](uint32_t slack) {
                     if (dbg >= 3) { if (st.cnt > (uint32_t)POOL - slack) st.cnt = 0; return; }   // measurement only
                     const uint32_t ep = *reinterpret_cast<volatile uint32_t *>(&S.cepoch[h]);
-                    const bool full = st.cnt > (uint32_t)POOL - slack || (st.cnt >= 192u && st.thr == __int_as_float(0x7f800000));
+                    // trigger: the pool must keep room for a stage (POOL - slack); a lower mark (`trig`) compacts earlier, which
+                    // costs more (cheap, one-query-at-a-time) compactions but lets a warming-up threshold tighten in smaller
+                    // steps: between compactions a lane admits D = trig - ~100 rows while the rows it has seen grow by the
+                    // factor 1 + D/100, i.e. D / ln(1 + D/100) survivors per e-fold of rows (211 at D = 284, 144 at D = 100)
+                    const bool full = st.cnt > min((uint32_t)POOL - slack, trig) || (st.cnt >= 192u && st.thr == __int_as_float(0x7f800000));
                     bool own, join = false;
                     if (ep == my_ep) {                                // the common case costs one vote
                         own = __any_sync(FULL, full);
@@ -1060,6 +1065,11 @@ cudaError_t launch_tile_tensor(hvs_engine *e, const float *queries_dev, const QS
         uint32_t kn = (uint32_t)(k >= K && k <= POOL - 128 ? k : 256);     // measured: 256 takes the (C,T) head group from 8.9 to 5.8 Mcycles per warp
         const char *ss = getenv("HVS_K3_SPARSE_SEL");
         if (ss && ss[0] == '0') kn |= 0x10000u;
+        const char *tg = getenv("HVS_K3_TRIG");
+        int tv = tg ? atoi(tg) : 0;
+        if (!(tv >= 128 && tv <= POOL - 128)) tv = POOL - 128;
+        kn |= (uint32_t)tv << 20;
+        if ((kn & 0xffffu) > (uint32_t)tv) kn = (kn & ~0xffffu) | (uint32_t)tv;       // lanes at the mark must take part
         const char *lh = getenv("HVS_K3_L2HINTS");
         if (lh && lh[0] == '1') kn |= 0x40000u;
         const char *hm = getenv("HVS_K3_HALF_MMA");
