@@ -171,6 +171,13 @@ HVS_API int hvs_solve_device(hvs_engine *e, const float *queries_dev, uint32_t m
  */
 HVS_API int hvs_solve_shard_device(hvs_engine *e, const float *queries_dev, uint32_t m, uint32_t rank, uint32_t world,
                                    uint32_t *out_ids_dev, uint32_t *out_order_host, uint32_t *out_counts_host);
+/*
+ * After the all-gather: rank r's rows arrive at gathered[r * cap ...][counts[r]] (cap = rows every rank contributed,
+ * >= max(counts)); this places every row at its query's position: out_ids[order[p]] = row p of the rank-major sequence.
+ * Uses the assignment of this engine's last hvs_solve_shard_device (kept on the device).  Device pointers;
+ * out_ids_dev: m x 100.  Enqueued on the engine's stream, returns without synchronising.
+ */
+HVS_API int hvs_shard_scatter_device(hvs_engine *e, const uint32_t *gathered_dev, uint32_t cap, uint32_t *out_ids_dev);
 /* The assignment alone, from slices (arena 0 = T-ordered, 1 = (C,T)-ordered; rows [begin,end)); CPU only. */
 HVS_API int hvs_shard_assign_host(const uint32_t *arena, const uint32_t *begin, const uint32_t *end, uint32_t m,
                                   uint32_t world, uint32_t *out_order, uint32_t *out_counts);

@@ -37,7 +37,7 @@ HVS_OK, HVS_ERR_INVALID, HVS_ERR_NO_DEVICE, HVS_ERR_CUDA, HVS_ERR_STATE, HVS_ERR
 ABI_SYMBOLS = (
     "hvs_abi_version", "hvs_last_error", "hvs_create", "hvs_destroy", "hvs_set_mode", "hvs_index_build", "hvs_index_build_device",
     "hvs_index_build_rows", "hvs_index_build_from_file",
-    "hvs_solve", "hvs_solve_full", "hvs_solve_device", "hvs_solve_shard_device", "hvs_shard_assign_host",
+    "hvs_solve", "hvs_solve_full", "hvs_solve_device", "hvs_solve_shard_device", "hvs_shard_scatter_device", "hvs_shard_assign_host",
     "hvs_solve_partial_device", "hvs_merge_partials_device", "hvs_rescore",
     "hvs_get_stats", "hvs_measure_ffma_peak", "hvs_plan_dryrun",
 )
@@ -111,6 +111,8 @@ def lib():
             f.argtypes = [vp, vp, u32, vp]
         L.hvs_solve_shard_device.restype = i32
         L.hvs_solve_shard_device.argtypes = [vp, vp, u32, u32, u32, vp, vp, vp]
+        L.hvs_shard_scatter_device.restype = i32
+        L.hvs_shard_scatter_device.argtypes = [vp, vp, u32, vp]
         L.hvs_shard_assign_host.restype = i32
         L.hvs_shard_assign_host.argtypes = [vp, vp, vp, u32, u32, vp, vp]
         L.hvs_solve_partial_device.restype = i32
@@ -231,6 +233,12 @@ class Engine:
         self._ck(lib().hvs_solve_shard_device(self._h, _dev_ptr(queries_dev, "float32", m * QROW), m, rank, world,
                                               _dev_ptr(out_dev, "int32", m * K), order.ctypes.data, counts.ctypes.data))
         return order, counts
+
+    def shard_scatter_device(self, gathered_dev, cap: int, out_dev) -> None:
+        """After the all-gather of solve_shard_device's rows (rank r's at gathered[r * cap ...]): every row to its
+        query's position in out_dev[m, 100] (hvs_shard_scatter_device; enqueued on the engine's stream)."""
+        self._ck(lib().hvs_shard_scatter_device(self._h, _dev_ptr(gathered_dev, "int32", cap * K), cap,
+                                                _dev_ptr(out_dev, "int32", K)))
 
     def solve_partial_device(self, queries_dev, out_dist_dev, out_ids_dev, out_count_dev) -> None:
         m = queries_dev.shape[0]

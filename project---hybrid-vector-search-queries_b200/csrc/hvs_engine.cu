@@ -649,12 +649,20 @@ extern "C" int hvs_solve_shard_device(hvs_engine *e, const float *queries_dev, u
         shard_assign(e->h_slices.as<QSlice>(), m, world, out_order_host, out_counts_host);        // the same on every rank
         for (uint32_t r = 0; r < rank; ++r) off += out_counts_host[r];
         m_own = out_counts_host[rank];
+        // keep the assignment on the device too (hvs_shard_scatter_device)
+        ECUDA(e->pdev.sa_order.ensure((size_t)m * 4));
+        ECUDA(e->pdev.sa_counts.ensure(256 * 4));
+        ECUDA(cudaMemcpyAsync(e->pdev.sa_order.p, out_order_host, (size_t)m * 4, cudaMemcpyHostToDevice, s));
+        ECUDA(cudaMemcpyAsync(e->pdev.sa_counts.p, out_counts_host, (size_t)world * 4, cudaMemcpyHostToDevice, s));
+        ECUDA(cudaStreamSynchronize(s));            // caller-owned pageable arrays
         ECUDA(e->d_shard_own.ensure((size_t)m_own * 4 + 16));
         ECUDA(e->h_stage_own.ensure((size_t)m_own * 4 + 16));
         std::memcpy(e->h_stage_own.p, out_order_host + off, (size_t)m_own * 4);
         ECUDA(cudaMemcpyAsync(e->d_shard_own.p, e->h_stage_own.p, (size_t)m_own * 4, cudaMemcpyHostToDevice, s));
         own_dev = e->d_shard_own.as<uint32_t>();
     }
+    e->shard_m = m;
+    e->shard_world = world;
     reset_solve_stats(e, m_own);
     e->stats.launches = on_device ? 6 : 1;
     if (m_own) {
@@ -675,6 +683,18 @@ extern "C" int hvs_solve_shard_device(hvs_engine *e, const float *queries_dev, u
     }
     e->stats.ms_solve_wall = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return rc;
+}
+
+extern "C" int hvs_shard_scatter_device(hvs_engine *e, const uint32_t *gathered_dev, uint32_t cap, uint32_t *out_ids_dev)
+{
+    if (!e) return HVS_ERR_INVALID;
+    e->err.clear();
+    if (!e->shard_m || !e->shard_world) EFAIL(HVS_ERR_STATE, "hvs_shard_scatter_device: no hvs_solve_shard_device before it");
+    if (!gathered_dev || !out_ids_dev || !cap) EFAIL(HVS_ERR_INVALID, "hvs_shard_scatter_device: NULL buffer or cap == 0");
+    ECUDA(cudaSetDevice(e->device));
+    ECUDA(launch_shard_scatter(e, gathered_dev, cap, e->pdev.sa_order.as<uint32_t>(), e->pdev.sa_counts.as<uint32_t>(), e->shard_m,
+                               e->shard_world, out_ids_dev));
+    return HVS_OK;
 }
 
 extern "C" int hvs_solve_full(hvs_engine *e, const float *queries_host, uint32_t m, uint32_t *out_ids_host, float *out_dist_host)

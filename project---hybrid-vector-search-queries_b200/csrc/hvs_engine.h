@@ -226,6 +226,7 @@ struct hvs_engine {
     hvs::HostPinned h_slices, h_flags, h_stage_own, h_stage, h_ingest[2];
     cudaEvent_t ev[12]{};
     cudaEvent_t evg[16]{};     // start/end of each group's tile launch
+    uint32_t shard_m = 0, shard_world = 0;        // the last hvs_solve_shard_device: its assignment stays in pdev.sa_order / sa_counts
     hvs::Plan plan;
     hvs::PlanDev pdev;
     hvs::HostPinned h_header;
@@ -275,6 +276,8 @@ cudaError_t plan_dev_redo(hvs_engine *e, const uint32_t *flags_dev, uint32_t n_t
 cudaError_t shard_assign_dev(hvs_engine *e, const QSlice *d_sl, uint32_t m, uint32_t world, uint32_t stripes,
                              uint32_t **order_dev, uint32_t **counts_dev);
 uint32_t shard_stripes(uint32_t m, uint32_t world);
+cudaError_t launch_shard_scatter(hvs_engine *e, const uint32_t *gathered_dev, uint32_t cap, const uint32_t *order_dev,
+                                 const uint32_t *counts_dev, uint32_t m, uint32_t world, uint32_t *out_ids_dev);
 cudaError_t direct_init_attributes();
 cudaError_t tile_ffma_init_attributes();
 cudaError_t tile_tensor_init_attributes();

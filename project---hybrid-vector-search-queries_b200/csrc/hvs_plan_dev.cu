@@ -406,6 +406,27 @@ __global__ void __launch_bounds__(SCAN_T) k_sa_assign(const QSlice *__restrict__
     if (threadIdx.x < world) counts[threadIdx.x] = scnt[threadIdx.x];
 }
 
+// one warp per row of the rank-major sequence: find its rank from the counts, copy its 400 bytes to the query's position
+__global__ void k_shard_scatter(const uint32_t *__restrict__ gathered, uint32_t cap, const uint32_t *__restrict__ order,
+                                const uint32_t *__restrict__ counts, uint32_t m, uint32_t world, uint32_t *__restrict__ out)
+{
+    const uint32_t p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (p >= m) return;
+    uint32_t r = 0, off = 0;
+    while (r + 1 < world && p >= off + counts[r]) { off += counts[r]; ++r; }
+    const uint4 *src = reinterpret_cast<const uint4 *>(gathered + ((size_t)r * cap + (p - off)) * K);
+    uint4 *dst = reinterpret_cast<uint4 *>(out + (size_t)order[p] * K);
+    if (lane < K / 4) dst[lane] = src[lane];
+}
+
+cudaError_t launch_shard_scatter(hvs_engine *e, const uint32_t *gathered_dev, uint32_t cap, const uint32_t *order_dev,
+                                 const uint32_t *counts_dev, uint32_t m, uint32_t world, uint32_t *out_ids_dev)
+{
+    if (!m) return cudaSuccess;
+    k_shard_scatter<<<(unsigned)(((size_t)m * 32 + 255) / 256), 256, 0, e->stream>>>(gathered_dev, cap, order_dev, counts_dev, m, world, out_ids_dev);
+    return cudaGetLastError();
+}
+
 // ---- host side -------------------------------------------------------------------------------------------------------
 #define PDCK(call) do { cudaError_t _c = (call); if (_c != cudaSuccess) return _c; } while (0)
 

@@ -458,6 +458,19 @@ def test_sharded_solve_covers_the_batch(H, oracle, check, datagen):
                 assert e.stats()["m"] == len(own)
             assert (seen == 1).all()
             assert np.array_equal(got, want), world
+            # the engine's own placement kernel (what follows the NCCL all-gather in sharding.solve_sharded): rank r's rows at
+            # gathered[r * cap ...], garbage in the slack rows
+            cap = int(counts.max()) + 5
+            gath = torch.full((world * cap, 100), -3, dtype=torch.int32, device="cuda")
+            off = 0
+            for r in range(world):
+                own = order[off:off + int(counts[r])].astype(np.int64)
+                gath[r * cap: r * cap + len(own)] = torch.from_numpy(want[own].view(np.int32)).cuda()
+                off += int(counts[r])
+            placed = torch.full((m, 100), -1, dtype=torch.int32, device="cuda")
+            e.shard_scatter_device(gath, cap, placed)
+            torch.cuda.synchronize()
+            assert np.array_equal(placed.cpu().numpy().view(np.uint32), want), world
     ref = oracle.vec_query(d, q[:48], want_dist=False)
     p = check.compare(d, q[:48], ref, want[:48], rtol=RTOL)
     assert p.ok and p.dist_bit_identical_rows == 48, p.summary()

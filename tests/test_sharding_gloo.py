@@ -195,7 +195,17 @@ class _StubEngine:
         own = order[off:off + int(counts[rank])].astype(np.int64)
         out[: len(own)] = torch.from_numpy(own[:, None] + np.arange(100)[None, :]).to(torch.int32)
         out[len(own):] = -7                                 # stale rows beyond the rank's share must never be picked up
+        self.last = (order, counts)
         return order, counts
+
+    def shard_scatter_device(self, gathered, cap, out):
+        """hvs_shard_scatter_device restated: row j of rank r (gathered[r * cap + j]) goes to out[order[off_r + j]]."""
+        import torch
+        order, counts = self.last
+        off = 0
+        for r, c in enumerate(counts.tolist()):
+            out[torch.from_numpy(order[off:off + c].astype(np.int64))] = gathered[r * cap: r * cap + c]
+            off += c
 
 
 def _worker_sharded(rank, world, port, m, out_dir):
