@@ -19,8 +19,9 @@
 //   [host: header D2H]
 //   k_pd_fill      one CTA per chunk: the chunk's queries in (begin, end) order -> item_q, items, candidate-list CSR
 //
-// Item order: the (C,T) arena's items first (short category slices: every query in them is warming up its threshold,
-// they are the slowest items per row), then the T arena's, each in row order.  One persistent launch sweeps them all.
+// Item order: first the items in which slices BEGIN (their thresholds start cold: the slow items -- nearly all of the
+// (C,T) arena's, the T arena's first chunk, and the last item or two of every other chunk's list), then the items made
+// only of queries begun in earlier chunks, in chunk order ((C,T) arena, then T).  One persistent launch sweeps them all.
 #include <cub/device/device_radix_sort.cuh>
 
 #include "hvs_engine.h"
