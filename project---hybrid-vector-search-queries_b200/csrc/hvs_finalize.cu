@@ -7,6 +7,8 @@
 // (sequential fp32 sub/mul/add, include/baseline.hpp:53-64 -- bit-identical, hvs_common.cuh) and the
 // final 100 are chosen and ordered by (distance, id), then the pad rule (include/baseline.hpp:138-147)
 // is applied exactly as in the direct kernel.
+#include <cstdlib>
+
 #include "hvs_engine.h"
 #include "hvs_margin.cuh"
 #include "hvs_topk.cuh"
@@ -29,7 +31,7 @@ k_finalize(const float *__restrict__ queries, const QSlice *__restrict__ slices,
            const uint32_t *__restrict__ qoff, const uint32_t *__restrict__ qlists, const uint64_t *__restrict__ cand,
            const uint32_t *__restrict__ cand_cnt, uint32_t *__restrict__ flags, Arena a0, Arena a1,
            const float *__restrict__ tail, uint32_t n_total, uint32_t id_offset, float xnorm_max, float tensor_sx, int partial,
-           uint32_t *__restrict__ audit,
+           uint32_t *__restrict__ audit, const uint32_t *__restrict__ gthr,
            uint32_t *__restrict__ out_ids, float *__restrict__ out_dist, uint32_t *__restrict__ out_count)
 {
     __shared__ FinSmem S;
@@ -40,6 +42,10 @@ k_finalize(const float *__restrict__ queries, const QSlice *__restrict__ slices,
     const uint32_t len = sl.end - sl.begin;
     S.p1.init(tid);
     S.p2.init(tid);
+    // Start from what the sweep already knows: gthr[q] = (100-th best score over everything swept) + margin, so a list
+    // entry at or above it cannot be among the answers.  Most of a long slice's ~10^4 list entries (early chunks keep
+    // what was within THEIR local bound) are then skipped right here instead of going through the selection below.
+    if (tid == 0 && gthr) S.p1.thr = okey_inv(gthr[q]);
     if (tid < DIM / 4)
         reinterpret_cast<float4 *>(S.q)[tid] = reinterpret_cast<const float4 *>(queries + (size_t)q * QROW + 4)[tid];
     __syncthreads();
@@ -128,6 +134,12 @@ k_finalize(const float *__restrict__ queries, const QSlice *__restrict__ slices,
     finish_query(S.p2, S.q, A, len, tail, n_total, id_offset, q, partial != 0, out_ids, out_dist, out_count, tid, FT);
 }
 
+static bool finalize_use_gthr()
+{
+    static const bool v = [] { const char *s = getenv("HVS_K5_GTHR"); return !(s && s[0] == '0'); }();
+    return v;
+}
+
 cudaError_t launch_finalize(hvs_engine *e, const float *queries_dev, const QSlice *slices_dev, const uint32_t *tile_q_dev,
                             uint32_t n_tile_q, const uint32_t *qoff_dev, const uint32_t *qlists_dev, const uint64_t *cand_dev,
                             const uint32_t *cand_cnt_dev, uint32_t *flags_dev, bool partial, bool tensor_lists, uint32_t *out_ids,
@@ -138,7 +150,8 @@ cudaError_t launch_finalize(hvs_engine *e, const float *queries_dev, const QSlic
     k_finalize<<<n_tile_q, FT, 0, e->stream>>>(queries_dev, slices_dev, tile_q_dev, qoff_dev, qlists_dev, cand_dev, cand_cnt_dev,
                                                 flags_dev, ix.arena(0), ix.arena(1), ix.tail.as<float>(), ix.n_total, ix.id_offset,
                                                 ix.xnorm_max, tensor_lists ? ix.img_scale : 0.f, partial ? 1 : 0,
-                                                (e->flags & HVS_FLAG_MARGIN_AUDIT) ? e->d_audit.as<uint32_t>() : nullptr, out_ids,
+                                                (e->flags & HVS_FLAG_MARGIN_AUDIT) ? e->d_audit.as<uint32_t>() : nullptr,
+                                                finalize_use_gthr() ? e->d_gthr.as<uint32_t>() : nullptr, out_ids,
                                                 out_dist, out_count);
     return cudaGetLastError();
 }

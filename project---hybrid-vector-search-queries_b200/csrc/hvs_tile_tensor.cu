@@ -958,16 +958,23 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
                     const uint32_t maxc = __reduce_max_sync(FULL, st.cnt);
                     uint64_t *L = cand + (size_t)(it.out_off + qslot) * KOUT;
                     const uint64_t polw = l2_policy_evict_first();    // written once, read by K5 after the whole sweep: do not displace the image
+                    // only what is still below the query's global bound goes to K5 (which starts from the same bound and would
+                    // skip the rest anyway): the lists of a long slice's early chunks shrink, and so do K5's reads
+                    const uint32_t gk = (qslot < it.nq && dbg == 0) ? ld_relaxed_u32(&gthr[st.qid]) : 0xffffffffu;
+                    uint32_t w = 0;
                     for (uint32_t i0 = 0; i0 < maxc; i0 += 16) {      // batches of 16 loads in flight
                         uint64_t e[16];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) e[j] = __ldcg(mypool + (size_t)32 * (i0 + j));
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
-                            if (i0 + j < st.cnt) { if (l2_hints) st_u64_hint(L + i0 + j, e[j], polw); else L[i0 + j] = e[j]; }
+                            if (i0 + j < st.cnt && (uint32_t)(e[j] >> 32) < gk) {
+                                if (l2_hints) st_u64_hint(L + w, e[j], polw); else L[w] = e[j];
+                                ++w;
+                            }
                     }
+                    if (qslot < it.nq) cand_cnt[it.out_off + qslot] = w;
                 }
-                if (qslot < it.nq) cand_cnt[it.out_off + qslot] = st.cnt;
                 c_merge += TICK() - tm0;
             }
         }
