@@ -270,53 +270,16 @@ void plan_begin(const QSlice *sl, uint32_t m, const PlanParams &pp, Plan &P)
             order[a].push_back(i);
             maxend[a] = std::max(maxend[a], sl[i].end);
         }
-    // Chunk boundaries.  Default: multiples of R.  HVS_ALIGN_CHUNKS=1 (experimental, not measured yet): a boundary moves
-    // back to the row at which the most tile queries' slices begin (at least 8), if that keeps the chunk above R/2 rows -- slices that
-    // start at a boundary (categories in the (C,T) arena) are then not cut in two a few rows later.
-    static const bool align_chunks = [] { const char *v = getenv("HVS_ALIGN_CHUNKS"); return v && v[0] == '1'; }();
+    // Chunk boundaries: the multiples of R.  (Round 1 carried an experimental variant that moved boundaries to the rows
+    // where many slices begin -- category starts; measured in round 2: no gain in the sweep, +1.4 ms of planning; removed.)
     for (uint32_t a = 0; a < 2; ++a) {
         std::vector<uint32_t> &b = P.bnd[a];
         b.clear();
         if (order[a].empty()) continue;
         const uint32_t nchunk = (maxend[a] + R - 1) / R;
-        if (!align_chunks) {
-            for (uint32_t c = 0; c <= nchunk; ++c) b.push_back((uint32_t)std::min<uint64_t>((uint64_t)c * R, 0xffffffffull));
-        } else {
-            std::vector<uint32_t> begins;
-            for (uint32_t i : order[a]) begins.push_back(sl[i].begin);
-            std::sort(begins.begin(), begins.end());
-            uint64_t cur = 0;
-            b.push_back(0);
-            while (cur < maxend[a]) {
-                const uint64_t target = cur + R;
-                // among the rows in (cur + R/2, target] the one at which the most slices begin, if at least 8 do
-                auto lo_it = std::upper_bound(begins.begin(), begins.end(), (uint32_t)std::min<uint64_t>(cur + R / 2, 0xffffffffull));
-                auto hi_it = std::upper_bound(begins.begin(), begins.end(), (uint32_t)std::min<uint64_t>(target, 0xffffffffull));
-                uint64_t next = target;
-                size_t best = 7;
-                for (auto it = lo_it; it != hi_it;) {
-                    auto run_end = std::upper_bound(it, hi_it, *it);
-                    if ((size_t)(run_end - it) > best) { best = (size_t)(run_end - it); next = *it; }
-                    it = run_end;
-                }
-                cur = next;
-                b.push_back((uint32_t)std::min<uint64_t>(cur, 0xffffffffull));
-            }
-        }
+        for (uint32_t c = 0; c <= nchunk; ++c) b.push_back((uint32_t)std::min<uint64_t>((uint64_t)c * R, 0xffffffffull));
     }
-    P.uniform_chunks = !align_chunks;
-    if (align_chunks)
-        for (uint32_t a = 0; a < 2; ++a) {
-            const std::vector<uint32_t> &b = P.bnd[a];
-            std::vector<uint32_t> &lut = P.bnd_lut[a];
-            lut.clear();
-            if (b.empty()) continue;
-            uint32_t c = 0;
-            for (uint64_t row = 0; row <= (uint64_t)b.back(); row += 4096) {
-                while (c + 1 < b.size() - 1 && row >= b[c + 1]) ++c;
-                lut.push_back(c);
-            }
-        }
+    P.uniform_chunks = true;
     for (uint32_t a = 0; a < 2; ++a)
         for (uint32_t i : order[a]) incid += P.chunk_of(a, sl[i].end - 1) - P.chunk_of(a, sl[i].begin) + 1;
     P.incid = incid;

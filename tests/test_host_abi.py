@@ -116,28 +116,18 @@ def test_planner_tiny_job_goes_direct(H):
         assert kind.all() and len(items) > 0
 
 
-def test_planner_aligned_chunks_cover_rows_once():
-    """HVS_ALIGN_CHUNKS=1 (experimental chunk boundaries at the rows where many slices begin): items still cover every
-    (query, row) of the tile queries exactly once, no chunk exceeds R rows, and a category-sized slice is no longer cut
-    in two.  The switch is read once per process, hence the subprocess."""
-    import subprocess, sys, textwrap
-    code = textwrap.dedent(f"""
-        import sys, importlib, numpy as np
-        sys.path.insert(0, {ROOT!r})
-        H = importlib.import_module("project---hybrid-vector-search-queries_b200")
-        ncat, cs, per = 40, 100_000, 2000      # with one item per SM the chunk size is 131072 rows >= a category
-        m = ncat * per
-        arena = np.ones(m, np.uint32)
-        begin = (np.repeat(np.arange(ncat), per) * cs).astype(np.uint32)
-        end = (begin + cs).astype(np.uint32)
-        kind, items, pc = H.plan_dryrun(arena, begin, end, H.MODE_AUTO)
-        assert kind.all()
-        rows = (items[:, 2] - items[:, 1]).astype(np.int64)
-        nq = (items[:, 3] & 0xffff).astype(np.int64)
-        assert int((rows * nq).sum()) == m * cs == pc, (int((rows * nq).sum()), m * cs, pc)
-        assert len(items) == ncat * 8 and (rows == cs).all() and nq.max() == 256, (len(items), rows[:5], nq[:5])
-        print("OK")
-    """)
-    env = dict(os.environ, HVS_ALIGN_CHUNKS="1", HVS_ITEMS_PER_SM="1")
-    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
-    assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
+def test_planner_items_cover_rows_once(H):
+    """Host statement of the planner (hvs_plan_dryrun): category-sized slices cut at chunk boundaries -- the items cover
+    every (query, row) of the tile queries (an item sweeps the union of its queries' rows inside its chunk, so where a
+    chunk holds the end of one category and the start of the next a little is swept for nothing: < 2 % here)."""
+    ncat, cs, per = 40, 100_000, 2000
+    m = ncat * per
+    arena = np.ones(m, np.uint32)
+    begin = (np.repeat(np.arange(ncat), per) * cs).astype(np.uint32)
+    end = (begin + cs).astype(np.uint32)
+    kind, items, pc = H.plan_dryrun(arena, begin, end, H.MODE_AUTO)
+    assert kind.all()
+    rows = (items[:, 2] - items[:, 1]).astype(np.int64)
+    nq = (items[:, 3] & 0xffff).astype(np.int64)
+    assert int((rows * nq).sum()) == pc and m * cs <= pc <= 1.02 * m * cs, (int((rows * nq).sum()), m * cs, pc)
+    assert nq.max() == 256 and rows.max() <= (1 << 22)
