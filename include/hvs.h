@@ -166,6 +166,7 @@ HVS_API int hvs_solve_device(hvs_engine *e, const float *queries_dev, uint32_t m
  * `rank`.  No communication happens here: the caller combines the ranks' rows (Python: sharding.solve_sharded, one
  * NCCL all-gather).
  *   out_order_host  : m query indices, rank-major; rank r owns out_order[sum(counts[0..r)) ...][counts[r]]
+ *                     (may be NULL: the engine keeps the assignment on the device for hvs_shard_scatter_device)
  *   out_counts_host : world entries
  *   out_ids_dev     : counts[rank] x 100 uint32 -- row i = the answer of query out_order[offset(rank) + i]  (size it m x 100)
  */

@@ -223,15 +223,16 @@ class Engine:
         self._ck(lib().hvs_solve_device(self._h, _dev_ptr(queries_dev, "float32", m * QROW), m,
                                         _dev_ptr(out_dev, "int32", m * K)))
 
-    def solve_shard_device(self, queries_dev, rank: int, world: int, out_dev) -> tuple[np.ndarray, np.ndarray]:
+    def solve_shard_device(self, queries_dev, rank: int, world: int, out_dev, want_order: bool = True):
         """Query-sharded solve (hvs_solve_shard_device): this rank's share of the batch every rank passes.
-        -> (order[m] rank-major query indices, counts[world]); out_dev[:counts[rank]] holds the answers of
+        -> (order[m] rank-major query indices or None, counts[world]); out_dev[:counts[rank]] holds the answers of
         order[offset(rank):][:counts[rank]].  No communication: sharding.solve_sharded combines the ranks."""
         m = queries_dev.shape[0]
-        order = np.empty(m, np.uint32)
+        order = np.empty(m, np.uint32) if want_order else None
         counts = np.zeros(world, np.uint32)
         self._ck(lib().hvs_solve_shard_device(self._h, _dev_ptr(queries_dev, "float32", m * QROW), m, rank, world,
-                                              _dev_ptr(out_dev, "int32", m * K), order.ctypes.data, counts.ctypes.data))
+                                              _dev_ptr(out_dev, "int32", m * K), order.ctypes.data if want_order else None,
+                                              counts.ctypes.data))
         return order, counts
 
     def shard_scatter_device(self, gathered_dev, cap: int, out_dev) -> None:

@@ -618,7 +618,7 @@ extern "C" int hvs_solve_shard_device(hvs_engine *e, const float *queries_dev, u
     int rc = check_solve_args(e, queries_dev, m, out_ids_dev);
     if (rc) return rc;
     if (!world || world > 255 || rank >= world) EFAIL(HVS_ERR_INVALID, "hvs_solve_shard_device: need rank < world <= 255");
-    if (!out_counts_host || (m && !out_order_host)) EFAIL(HVS_ERR_INVALID, "hvs_solve_shard_device: NULL buffer");
+    if (!out_counts_host) EFAIL(HVS_ERR_INVALID, "hvs_solve_shard_device: NULL buffer");
     auto t0 = std::chrono::steady_clock::now();
     e->stats.ms_h2d = e->stats.ms_d2h = 0.f;
     reset_solve_stats(e, 0);
@@ -640,10 +640,10 @@ extern "C" int hvs_solve_shard_device(hvs_engine *e, const float *queries_dev, u
         ECUDA(shard_assign_dev(e, d_sl_all, m, world, stripes, &order_dev, &counts_dev));
         ECUDA(e->h_stage_own.ensure((size_t)m * 4 + 256 * 4));
         uint32_t *h_order = e->h_stage_own.as<uint32_t>(), *h_counts = h_order + m;
-        ECUDA(cudaMemcpyAsync(h_order, order_dev, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
+        if (out_order_host) ECUDA(cudaMemcpyAsync(h_order, order_dev, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
         ECUDA(cudaMemcpyAsync(h_counts, counts_dev, (size_t)world * 4, cudaMemcpyDeviceToHost, s));
         ECUDA(cudaStreamSynchronize(s));
-        std::memcpy(out_order_host, h_order, (size_t)m * 4);
+        if (out_order_host) std::memcpy(out_order_host, h_order, (size_t)m * 4);
         std::memcpy(out_counts_host, h_counts, (size_t)world * 4);
         for (uint32_t r = 0; r < rank; ++r) off += out_counts_host[r];
         m_own = out_counts_host[rank];
@@ -651,6 +651,8 @@ extern "C" int hvs_solve_shard_device(hvs_engine *e, const float *queries_dev, u
     } else {
         ECUDA(cudaMemcpyAsync(e->h_slices.p, d_sl_all, (size_t)m * sizeof(QSlice), cudaMemcpyDeviceToHost, s));
         ECUDA(cudaStreamSynchronize(s));
+        e->h_shard_order.resize(m);
+        if (!out_order_host) out_order_host = e->h_shard_order.data();
         shard_assign(e->h_slices.as<QSlice>(), m, world, out_order_host, out_counts_host);        // the same on every rank
         for (uint32_t r = 0; r < rank; ++r) off += out_counts_host[r];
         m_own = out_counts_host[rank];

@@ -58,7 +58,7 @@ def solve_sharded(engine, queries_dev, rank: int, world: int, scratch=None):
         sc.clear()
         sc.update(m=m, world=world, own=torch.empty((m, 100), dtype=torch.int32, device=dev),
                   out=torch.empty((m, 100), dtype=torch.int32, device=dev))
-    order, counts = engine.solve_shard_device(queries_dev, rank, world, sc["own"])
+    _, counts = engine.solve_shard_device(queries_dev, rank, world, sc["own"], want_order=False)
     longest = int(counts.max()) if m else 0
     if sc.get("cap", -1) < longest or "gath" not in sc:    # rows every rank contributes to the gather (same on all ranks)
         sc["cap"] = max(1, min(m, longest + longest // 8 + 8))

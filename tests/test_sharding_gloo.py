@@ -188,7 +188,7 @@ class _StubEngine:
     def __init__(self, hvs, arena, begin, end):
         self.hvs, self.sl = hvs, (arena, begin, end)
 
-    def solve_shard_device(self, q, rank, world, out):
+    def solve_shard_device(self, q, rank, world, out, want_order=True):
         import torch
         order, counts = self.hvs.shard_assign(*self.sl, world)
         off = int(counts[:rank].sum())
