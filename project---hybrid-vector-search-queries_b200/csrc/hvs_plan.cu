@@ -252,10 +252,7 @@ void plan_begin(const QSlice *sl, uint32_t m, const PlanParams &pp, Plan &P)
 
     // chunk size: aim at ~16 items per SM over the whole job, power of two
     static const uint32_t ips = [] { const char *v = getenv("HVS_ITEMS_PER_SM"); int k = v ? atoi(v) : 0; return (uint32_t)(k > 0 ? k : 16); }();
-    uint64_t want = tile_qrows / ((uint64_t)BQ * ips * 148);
-    uint32_t R = 8192;
-    while ((uint64_t)R * 2 <= want) R *= 2;
-    if (R > (1u << 22)) R = 1u << 22;
+    const uint32_t R = plan_chunk_rows(tile_qrows, BQ, ips, 148);
     P.R = R;
 
     lap("chunking");

@@ -139,11 +139,7 @@ __global__ void k_pd_params(PlanCfg cfg, PlanHeader *__restrict__ H)
     unsigned long long rows = H->tile_qrows;
     if (rows && rows < cfg.min_tile_pairs && !cfg.force_tile) { rows = 0; H->tile_qrows = 0; H->pairs_tile = 0; H->tiny = 1; }
     uint32_t R = 8192;
-    if (rows) {
-        const unsigned long long want = rows / ((unsigned long long)cfg.bq * cfg.items_per_sm * cfg.sm_count);
-        while ((unsigned long long)R * 2 <= want) R *= 2;
-        if (R > (1u << 22)) R = 1u << 22;
-    }
+    if (rows) R = plan_chunk_rows(rows, cfg.bq, cfg.items_per_sm, cfg.sm_count);
     H->R = R;
     H->Ra[0] = R;
     H->Ra[1] = R < cfg.ct_min_rows ? cfg.ct_min_rows : R;

@@ -119,7 +119,7 @@ def test_planner_tiny_job_goes_direct(H):
 def test_planner_items_cover_rows_once(H):
     """Host statement of the planner (hvs_plan_dryrun): category-sized slices cut at chunk boundaries -- the items cover
     every (query, row) of the tile queries (an item sweeps the union of its queries' rows inside its chunk, so where a
-    chunk holds the end of one category and the start of the next a little is swept for nothing: < 2 % here)."""
+    chunk holds the end of one category and the start of the next a little is swept for nothing: < 3 % here)."""
     ncat, cs, per = 40, 100_000, 2000
     m = ncat * per
     arena = np.ones(m, np.uint32)
@@ -129,5 +129,5 @@ def test_planner_items_cover_rows_once(H):
     assert kind.all()
     rows = (items[:, 2] - items[:, 1]).astype(np.int64)
     nq = (items[:, 3] & 0xffff).astype(np.int64)
-    assert int((rows * nq).sum()) == pc and m * cs <= pc <= 1.02 * m * cs, (int((rows * nq).sum()), m * cs, pc)
+    assert int((rows * nq).sum()) == pc and m * cs <= pc <= 1.03 * m * cs, (int((rows * nq).sum()), m * cs, pc)
     assert nq.max() == 256 and rows.max() <= (1 << 22)

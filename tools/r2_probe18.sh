@@ -1,0 +1,2 @@
+#!/bin/bash
+for W in 8 4; do for ips in 16 8 4; do HVS_ITEMS_PER_SM=$ips python tools/shard_rank_probe.py $W 0 2>&1 | tail -1; done; done
