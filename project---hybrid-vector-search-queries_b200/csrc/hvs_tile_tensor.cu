@@ -66,6 +66,9 @@ constexpr int A_B = 128 * ROW_B;      // one query half
                                       // 36.7 ms instead of 33.9 -- twice the MMA instructions re-read the A operand twice as often and the
                                       // barrier traffic doubles, which costs more than the finer hand-off wins.  Kept as a build option.
 #endif
+#ifndef HVS_K3_LD2
+#define HVS_K3_LD2 0
+#endif
 constexpr int NACC = HVS_K3_ACC64 ? 4 : 2;     // accumulator buffers per query half
 constexpr int ACCN = HVS_K3_ACC64 ? 64 : 128;  // data rows (TMEM columns) per accumulator == MMA N
 constexpr int NTHR = 352;              // warp 0 TMA, warp 1 MMA issuer of query half 0, warps 2..9 epilogue, warp 10 MMA issuer of half 1
@@ -903,6 +906,19 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
                         make_room(128u);
                         thr_s = (trow0 < st.qhi && trow0 + TN > st.qlo) ? st.thr : __int_as_float(0xff800000);
                         uint32_t ra[32], rb[32];
+#if HVS_K3_LD2
+                        // two loads in flight, two waits per stage (tcgen05.wait::ld waits for every outstanding load)
+                        tmem_ld32(tcol, ra);
+                        tmem_ld32(tcol + 32, rb);
+                        tmem_wait_ld();
+                        scan(ra, trow0);
+                        tmem_ld32(tcol + 64, ra);
+                        scan(rb, trow0 + 32);
+                        tmem_ld32(tcol + 96, rb);
+                        tmem_wait_ld();
+                        scan(ra, trow0 + 64);
+                        scan(rb, trow0 + 96);
+#else
                         tmem_ld32(tcol, ra);
                         tmem_wait_ld();
                         tmem_ld32(tcol + 32, rb);
@@ -915,6 +931,7 @@ k_tile_tensor(const float *__restrict__ queries, const QSlice *__restrict__ slic
                         scan(ra, trow0 + 64);
                         tmem_wait_ld();
                         scan(rb, trow0 + 96);
+#endif
                     } else if (dbg == 0) {
 #pragma unroll 1
                         for (int c4 = 0; c4 < TN / 32; ++c4) {
