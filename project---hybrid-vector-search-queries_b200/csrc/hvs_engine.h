@@ -91,7 +91,10 @@ constexpr int KOUT = 256;        // candidates an item hands to finalize per que
 #define HVS_POOL 512
 #endif
 constexpr int TENSOR_POOL = HVS_POOL; // K3: survivor pool entries per (CTA, query) in global memory
-constexpr int TENSOR_GBEST = 128;
+#ifndef HVS_GBEST
+#define HVS_GBEST 128
+#endif
+constexpr int TENSOR_GBEST = HVS_GBEST;
 constexpr uint32_t SMALL_MAX = 255;  // K4s: slices of at most this many rows get a warp each (8 rounds of 32 rows; must stay below PlanParams::min_tile_len:
                                      // never tile queries).  Longer sparse slices take the CTA-per-query scan, which has the lower latency per query.
 constexpr int OUTLIER_MAX = 256;  // K0: most rows that may be set aside as norm outliers // K3: per-query global list of the best scores seen by any CTA

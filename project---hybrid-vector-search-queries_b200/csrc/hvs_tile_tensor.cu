@@ -75,6 +75,8 @@ constexpr int NTHR = 352;              // warp 0 TMA, warp 1 MMA issuer of query
 constexpr int POOL = TENSOR_POOL;     // survivor pool entries per query (global memory)
 constexpr uint32_t FULL = 0xffffffffu;
 constexpr int GB = TENSOR_GBEST;      // per-query global list of best scores over all finished chunks
+constexpr int GPL = GB / 32;          // list scores per lane when a warp holds one query's list in registers
+static_assert(GB % 32 == 0 && GB >= 128 && GB <= 512, "global list size");
 constexpr int SPARSE_LANES = 6;
 constexpr int SPARSE_SEL = 8;         // merge_global: up to this many lanes whose global list needs a new K-th best are handled one query at a time       // compaction: up to this many participating lanes are handled one query at a time by the whole warp
 
@@ -396,14 +398,14 @@ __device__ __noinline__ float merge_global(uint32_t cnt, float thr, float margin
             const float margin_src = __shfl_sync(FULL, margin, src), thr_src = __shfl_sync(FULL, thr, src);
             uint32_t *Gs = gbest + (size_t)q_src * GB;
             const uint32_t *scs = reinterpret_cast<const uint32_t *>(pool_warp) + 2 * src + 1;
-            uint32_t e[12];                                                  // 4 list scores + 8 pool scores per lane; 0xffffffff = none
+            uint32_t e[GPL + 8];                                             // GB/32 list scores + 8 pool scores per lane; 0xffffffff = none
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { const uint32_t i = (uint32_t)lane + 32u * j; e[j] = i < g_n ? __ldcg(Gs + i) : 0xffffffffu; }
+            for (int j = 0; j < GPL; ++j) { const uint32_t i = (uint32_t)lane + 32u * j; e[j] = i < g_n ? __ldcg(Gs + i) : 0xffffffffu; }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { const uint32_t i = (uint32_t)lane + 32u * j; e[4 + j] = i < c ? __ldcg(scs + (size_t)64 * i) : 0xffffffffu; }
+            for (int j = 0; j < 8; ++j) { const uint32_t i = (uint32_t)lane + 32u * j; e[GPL + j] = i < c ? __ldcg(scs + (size_t)64 * i) : 0xffffffffu; }
             uint32_t klo = 0xffffffffu, khi = 0u;
 #pragma unroll
-            for (int j = 0; j < 12; ++j)
+            for (int j = 0; j < GPL + 8; ++j)
                 if (e[j] != 0xffffffffu) { klo = min(klo, e[j]); khi = max(khi, e[j]); }
             klo = __reduce_min_sync(FULL, klo);
             khi = __reduce_max_sync(FULL, khi);
@@ -414,7 +416,7 @@ __device__ __noinline__ float merge_global(uint32_t cnt, float thr, float margin
                     const uint32_t mid = select_probe(klo, khi, clo, chi, it);
                     uint32_t n = 0;
 #pragma unroll
-                    for (int j = 0; j < 12; ++j) n += (e[j] <= mid) ? 1u : 0u;      // 0xffffffff never counts: mid < khi <= 0xfffffffe
+                    for (int j = 0; j < GPL + 8; ++j) n += (e[j] <= mid) ? 1u : 0u;      // 0xffffffff never counts: mid < khi <= 0xfffffffe
                     n = __reduce_add_sync(FULL, n);
                     if (n >= (uint32_t)K) { khi = mid; chi = n; if (n <= (uint32_t)K + 8u) break; }
                     else { klo = mid; clo = n; }
@@ -422,7 +424,7 @@ __device__ __noinline__ float merge_global(uint32_t cnt, float thr, float margin
             }
             uint32_t kc = 0;
 #pragma unroll
-            for (int j = 0; j < 12; ++j) kc += (e[j] != 0xffffffffu && e[j] <= khi) ? 1u : 0u;
+            for (int j = 0; j < GPL + 8; ++j) kc += (e[j] != 0xffffffffu && e[j] <= khi) ? 1u : 0u;
             uint32_t pos = kc;                                               // inclusive scan over the lanes
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL, pos, o); if (lane >= o) pos += v; }
@@ -430,7 +432,7 @@ __device__ __noinline__ float merge_global(uint32_t cnt, float thr, float margin
             pos -= kc;
             __syncwarp();                                                    // every lane holds its share: the list may be rewritten
 #pragma unroll
-            for (int j = 0; j < 12; ++j)
+            for (int j = 0; j < GPL + 8; ++j)
                 if (e[j] != 0xffffffffu && e[j] <= khi) { if (pos < (uint32_t)GB) Gs[pos] = e[j]; ++pos; }
             __threadfence();
             __syncwarp();
