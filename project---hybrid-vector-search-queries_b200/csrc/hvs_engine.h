@@ -284,6 +284,11 @@ cudaError_t launch_merge_partials(hvs_engine *e, const float *queries_dev, uint3
 cudaError_t launch_rescore(hvs_engine *e, const float *queries_dev, uint32_t m, const uint32_t *ids_dev, float *out_dev,
                            const float *rows_unused);
 cudaError_t measure_ffma_peak(hvs_engine *e, uint32_t iters, float *tflops, float *mhz);
+// hvs_sort.cu: stable LSD radix sort of (key, u32 value) pairs by key bits [0, end_bit); (k0, v0) = input AND scratch, the
+// result lands in (k1, v1); tmp = radix_sort_temp_bytes(n) bytes
+size_t radix_sort_temp_bytes(uint32_t n);
+template <class KeyT>
+cudaError_t radix_sort_pairs(KeyT *k0, uint32_t *v0, KeyT *k1, uint32_t *v1, uint32_t n, int end_bit, void *tmp, cudaStream_t st);
 // device planner: everything up to the header read-back (one stream sync); then the chunk lists, items and K5's list index
 cudaError_t plan_dev_begin(hvs_engine *e, const QSlice *d_sl, uint32_t m, const PlanCfg &cfg, PlanHeader *h_out);
 cudaError_t plan_dev_fill(hvs_engine *e, const QSlice *d_sl, const PlanHeader &h, const PlanCfg &cfg, uint32_t *item_q_dev,

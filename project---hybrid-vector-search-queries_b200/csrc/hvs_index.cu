@@ -5,14 +5,13 @@
 // re-laid-out copies of D so that every predicate is one contiguous row range:
 //   arena T  : rows ordered by ord(T)               -> types 0 (all rows) and 2 (l <= T <= r)
 //   arena CT : rows ordered by ord(C)<<32 | ord(T)  -> types 1 (C == v) and 3 (C == v, l <= T <= r)
+// The sorts are the hand-written LSD radix sort of hvs_sort.cu.
 // Each arena holds the 100-d vectors as contiguous 400-byte rows (16-byte aligned, so a tile of
 // consecutive rows is ONE contiguous block that the TMA engine moves with a single 1-D bulk copy),
 // the original row ids, ||x||^2, and the sorted keys for binary search.  Never sees queries
 // (contest rule, README.md:68).  HBM-bound: ~2 sorts + 2 gathers of 400 B/row.
 #include <algorithm>
 #include <cmath>
-
-#include <cub/device/device_radix_sort.cuh>
 
 #include "hvs_engine.h"
 
@@ -28,6 +27,12 @@ __global__ void k_make_keys(const float *__restrict__ rows, uint32_t n, uint32_t
     key_t[j] = kt;
     key_ct[j] = ((uint64_t)kc << 32) | kt;
     perm[j] = j;
+}
+
+__global__ void k_iota(uint32_t *__restrict__ p, uint32_t n)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = i;
 }
 
 // One warp per destination row: gather the vector of source row perm[p] into arena row p,
@@ -156,22 +161,19 @@ cudaError_t index_build_device(hvs_engine *e, const float *rows, uint32_t n_tota
 
     if (n) {
         k_make_keys<<<(n + 255) / 256, 256, 0, st>>>(rows, n, key_t_in.as<uint32_t>(), key_ct_in.as<uint64_t>(), perm_in.as<uint32_t>());
-        size_t tb1 = 0, tb2 = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, tb1, key_t_in.as<uint32_t>(), ix.keys_t.as<uint32_t>(), perm_in.as<uint32_t>(), perm_out.as<uint32_t>(), (int)n, 0, 32, st);
-        cub::DeviceRadixSort::SortPairs(nullptr, tb2, key_ct_in.as<uint64_t>(), ix.keys_ct.as<uint64_t>(), perm_in.as<uint32_t>(), perm_out.as<uint32_t>(), (int)n, 0, 64, st);
-        cudaError_t c = tmp.ensure(tb1 > tb2 ? tb1 : tb2);
-        if (c != cudaSuccess) fail(c, "cub temp alloc");
+        cudaError_t c = tmp.ensure(radix_sort_temp_bytes(n));
+        if (c != cudaSuccess) fail(c, "sort temp alloc");
         const unsigned gather_blocks = (unsigned)(((size_t)n * 32 + 255) / 256);
         if (rc == cudaSuccess) {
-            size_t tb = tmp.cap;
-            c = cub::DeviceRadixSort::SortPairs(tmp.p, tb, key_t_in.as<uint32_t>(), ix.keys_t.as<uint32_t>(), perm_in.as<uint32_t>(), perm_out.as<uint32_t>(), (int)n, 0, 32, st);
+            // (key_t_in, perm_in) are the sort's scratch afterwards: the row permutation is written afresh for the second sort
+            c = radix_sort_pairs<uint32_t>(key_t_in.as<uint32_t>(), perm_in.as<uint32_t>(), ix.keys_t.as<uint32_t>(), perm_out.as<uint32_t>(), n, 32, tmp.p, st);
             if (c != cudaSuccess) fail(c, "radix sort (T)");
             k_gather<<<gather_blocks, 256, 0, st>>>(rows, perm_out.as<uint32_t>(), n, ix.id_offset, ix.x[ARENA_T].as<float>(),
                                                      ix.ids[ARENA_T].as<uint32_t>(), ix.xnorm[ARENA_T].as<float>(), ix.inv_t.as<uint32_t>());
         }
         if (rc == cudaSuccess) {
-            size_t tb = tmp.cap;
-            c = cub::DeviceRadixSort::SortPairs(tmp.p, tb, key_ct_in.as<uint64_t>(), ix.keys_ct.as<uint64_t>(), perm_in.as<uint32_t>(), perm_out.as<uint32_t>(), (int)n, 0, 64, st);
+            k_iota<<<(n + 255) / 256, 256, 0, st>>>(perm_in.as<uint32_t>(), n);
+            c = radix_sort_pairs<uint64_t>(key_ct_in.as<uint64_t>(), perm_in.as<uint32_t>(), ix.keys_ct.as<uint64_t>(), perm_out.as<uint32_t>(), n, 64, tmp.p, st);
             if (c != cudaSuccess) fail(c, "radix sort (C,T)");
             k_gather<<<gather_blocks, 256, 0, st>>>(rows, perm_out.as<uint32_t>(), n, ix.id_offset, ix.x[ARENA_CT].as<float>(),
                                                      ix.ids[ARENA_CT].as<uint32_t>(), ix.xnorm[ARENA_CT].as<float>(), nullptr);

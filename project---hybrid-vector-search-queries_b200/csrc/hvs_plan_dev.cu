@@ -13,7 +13,7 @@
 //   k_pd_classify  per query: average depth over its slice >= need -> tile query; pair totals
 //   k_pd_params    one thread: tiny-job rule, chunk size R
 //   k_pd_keys      sort key per query: class | arena | begin | end   (tile queries first, then CTA-scan queries)
-//   (radix sort of m 64-bit keys: cub::DeviceRadixSort, as in K0)
+//   (radix sort of m 64-bit keys: hvs_sort.cu, the sort of K0)
 //   k_pd_chunks    tile queries -> chunk occupancy (difference array), nchunks per query
 //   k_pd_scan      one CTA: occupancy -> per-chunk list offsets and item offsets; per-query candidate-list offsets
 //   [host: header D2H]
@@ -22,8 +22,6 @@
 // Item order: first the items in which slices BEGIN (their thresholds start cold: the slow items -- nearly all of the
 // (C,T) arena's, the T arena's first chunk, and the last item or two of every other chunk's list), then the items made
 // only of queries begun in earlier chunks, in chunk order ((C,T) arena, then T).  One persistent launch sweeps them all.
-#include <cub/device/device_radix_sort.cuh>
-
 #include "hvs_engine.h"
 
 namespace hvs {
@@ -447,22 +445,15 @@ cudaError_t shard_assign_dev(hvs_engine *e, const QSlice *d_sl, uint32_t m, uint
     PDCK(P.sa_counts.ensure(256 * 4));
     const unsigned gb = (m + 255) / 256;
     k_sa_keys<<<gb, 256, 0, s>>>(d_sl, m, nb, P.keys_in.as<uint64_t>(), P.vals_in.as<uint32_t>());
-    size_t tb1 = 0, tb2 = 0;
     const int end_bit = (int)(2 * nb + 2);
-    PDCK(cub::DeviceRadixSort::SortPairs(nullptr, tb1, P.keys_in.as<uint64_t>(), P.keys.as<uint64_t>(), P.vals_in.as<uint32_t>(),
-                                         P.vals.as<uint32_t>(), (int)m, 0, end_bit, s));
-    PDCK(cub::DeviceRadixSort::SortPairs(nullptr, tb2, P.sa_owner_in.as<uint32_t>(), P.sa_owner.as<uint32_t>(), P.vals.as<uint32_t>(),
-                                         P.sa_order.as<uint32_t>(), (int)m, 0, 8, s));
-    PDCK(P.sort_tmp.ensure(tb1 > tb2 ? tb1 : tb2));
-    size_t tb = P.sort_tmp.cap;
-    PDCK(cub::DeviceRadixSort::SortPairs(P.sort_tmp.p, tb, P.keys_in.as<uint64_t>(), P.keys.as<uint64_t>(), P.vals_in.as<uint32_t>(),
-                                         P.vals.as<uint32_t>(), (int)m, 0, end_bit, s));
+    PDCK(P.sort_tmp.ensure(radix_sort_temp_bytes(m)));
+    PDCK(radix_sort_pairs<uint64_t>(P.keys_in.as<uint64_t>(), P.vals_in.as<uint32_t>(), P.keys.as<uint64_t>(), P.vals.as<uint32_t>(), m, end_bit,
+                                    P.sort_tmp.p, s));
     k_sa_assign<<<1, SCAN_T, 0, s>>>(d_sl, P.vals.as<uint32_t>(), m, world, stripes, shard_query_cost(), P.sa_owner_in.as<uint32_t>(),
                                      P.sa_counts.as<uint32_t>());
-    tb = P.sort_tmp.cap;
-    // stable sort by owner: rank-major, each rank's queries keep the (arena, begin, end) order
-    PDCK(cub::DeviceRadixSort::SortPairs(P.sort_tmp.p, tb, P.sa_owner_in.as<uint32_t>(), P.sa_owner.as<uint32_t>(), P.vals.as<uint32_t>(),
-                                         P.sa_order.as<uint32_t>(), (int)m, 0, 8, s));
+    // stable sort by owner (one 8-bit pass): rank-major, each rank's queries keep the (arena, begin, end) order
+    PDCK(radix_sort_pairs<uint32_t>(P.sa_owner_in.as<uint32_t>(), P.vals.as<uint32_t>(), P.sa_owner.as<uint32_t>(), P.sa_order.as<uint32_t>(), m, 8,
+                                    P.sort_tmp.p, s));
     PDCK(cudaGetLastError());
     *order_dev = P.sa_order.as<uint32_t>();
     *counts_dev = P.sa_counts.as<uint32_t>();
@@ -511,14 +502,10 @@ cudaError_t plan_dev_begin(hvs_engine *e, const QSlice *d_sl, uint32_t m, const 
     k_pd_classify<<<gb, 256, 0, s>>>(d_sl, m, pref0, pref1, cfg, P.cls.as<uint8_t>(), H);
     k_pd_params<<<1, 32, 0, s>>>(cfg, H);
     k_pd_keys<<<gb, 256, 0, s>>>(d_sl, m, P.cls.as<uint8_t>(), nb, H, P.keys_in.as<uint64_t>(), P.vals_in.as<uint32_t>());
-    size_t tb = 0;
     const int end_bit = (int)(2 * nb + 4);
-    PDCK(cub::DeviceRadixSort::SortPairs(nullptr, tb, P.keys_in.as<uint64_t>(), P.keys.as<uint64_t>(), P.vals_in.as<uint32_t>(),
-                                         P.vals.as<uint32_t>(), (int)m, 0, end_bit, s));
-    PDCK(P.sort_tmp.ensure(tb));
-    tb = P.sort_tmp.cap;
-    PDCK(cub::DeviceRadixSort::SortPairs(P.sort_tmp.p, tb, P.keys_in.as<uint64_t>(), P.keys.as<uint64_t>(), P.vals_in.as<uint32_t>(),
-                                         P.vals.as<uint32_t>(), (int)m, 0, end_bit, s));
+    PDCK(P.sort_tmp.ensure(radix_sort_temp_bytes(m)));
+    PDCK(radix_sort_pairs<uint64_t>(P.keys_in.as<uint64_t>(), P.vals_in.as<uint32_t>(), P.keys.as<uint64_t>(), P.vals.as<uint32_t>(), m, end_bit,
+                                    P.sort_tmp.p, s));
     k_pd_chunks<<<gb, 256, 0, s>>>(P.keys.as<uint64_t>(), P.vals.as<uint32_t>(), m, nb, d_sl, H, P.cdiff.as<int>(), P.cbeg.as<uint32_t>(),
                                    P.nch.as<uint32_t>());
     k_pd_scan<<<1, SCAN_T, 0, s>>>(H, P.cdiff.as<int>(), cfg.bq, P.cbeg.as<uint32_t>(), cfg.seed_phase, P.cstart.as<uint32_t>(), P.ibase.as<uint32_t>(),
