@@ -5,14 +5,17 @@
 //
 // One pass = three launches:
 //   k_rs_hist     every CTA counts the digits of its tile (4096 keys)                    -> hist[digit][cta]
-//   k_rs_scan     one CTA: exclusive scan over hist in (digit, cta) order                -> global base of every (digit, cta)
+//   k_rs_scan     one CTA per digit: exclusive scan of the digit's row of CTA counts, row total -> tot[digit]
+//                 (the scatter kernel scans the 256 totals itself: base of (digit, cta) = digits below + CTAs before)
 //   k_rs_scatter  every CTA re-reads its tile; each WARP owns 512 consecutive keys of it (16 rounds of 32): per-warp digit
 //                 counts -> bases per (warp, digit) in warp order -> each round ranks its keys inside the warp with
 //                 __match_any_sync (equal digits keep their lane order) and writes them out.  Tile order = CTA order, warp
 //                 order, round order, lane order = the input order: the sort is stable, which LSD needs.
-// HBM-bound (K0: 8 passes x ~32 B per key; 10^7 keys: a few ms, once per index build); launch-bound for the planner's
-// 4x10^4 keys (7 passes x 3 launches).
+// HBM-bound (K0: 8 passes x ~32 B per key; 10^7 keys: a few ms, once per index build).  Up to 65536 keys (the planner's
+// 4x10^4) all passes run in ONE launch of an 8-CTA cluster (k_rs_cluster below) instead of 7 x 3 launches.
 #include "hvs_engine.h"
+#include <cooperative_groups.h>
+#include <cstdlib>
 
 namespace hvs {
 
@@ -21,7 +24,6 @@ constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_ROUNDS = 16;                              // keys per lane
 constexpr int RS_TILE = RS_THREADS * RS_ROUNDS;            // 4096 keys per CTA
-constexpr int RS_SCAN_T = 1024;
 
 template <class KeyT>
 __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const KeyT *__restrict__ keys, uint32_t n, int shift, uint32_t nblocks,
@@ -40,38 +42,57 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const KeyT *__restrict__
     hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
 }
 
-// exclusive scan of `total` counters in place (one CTA; each thread owns a contiguous run)
-__global__ void __launch_bounds__(RS_SCAN_T) k_rs_scan(uint32_t *__restrict__ hist, uint32_t total)
+// exclusive scan of x over the CTA's NW warps; *total = the sum (sm: NW + 1 words)
+template <int NW>
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t x, uint32_t *sm, uint32_t *total)
 {
-    __shared__ uint32_t sm[33];
-    const uint32_t per = (total + RS_SCAN_T - 1) / RS_SCAN_T;
-    const uint32_t i0 = min(total, threadIdx.x * per), i1 = min(total, i0 + per);
-    uint32_t s = 0;
-    for (uint32_t i = i0; i < i1; ++i) s += hist[i];
-    // block exclusive scan of s
+    static_assert(NW <= 32 && (NW & (NW - 1)) == 0, "warp count: power of two, at most 32");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t x = s;
+    uint32_t inc = x;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-    if (lane == 31) sm[warp] = x;
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+    __syncthreads();                                          // sm may still be read from the previous call
+    if (lane == 31) sm[warp] = inc;
     __syncthreads();
     if (warp == 0) {
-        uint32_t w = sm[lane];
+        const uint32_t w = lane < NW ? sm[lane] : 0u;
+        uint32_t wi = w;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
-        sm[lane] = w;
+        for (int o = 1; o < NW; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += y; }
+        if (lane < NW) sm[lane] = wi - w;
+        if (lane == NW - 1) sm[NW] = wi;
     }
     __syncthreads();
-    uint32_t run = (warp ? sm[warp - 1] : 0u) + x - s;
-    for (uint32_t i = i0; i < i1; ++i) { const uint32_t c = hist[i]; hist[i] = run; run += c; }
+    *total = sm[NW];
+    return sm[warp] + inc - x;
+}
+
+// one CTA per digit: exclusive scan of the digit's row of per-CTA counts in place (coalesced, 256 at a time); the row's
+// total goes to tot[digit] -- the scatter kernel turns the 256 totals into digit bases itself
+__global__ void __launch_bounds__(RS_THREADS) k_rs_scan(uint32_t *__restrict__ hist, uint32_t nblocks, uint32_t *__restrict__ tot)
+{
+    __shared__ uint32_t sm[RS_WARPS + 1];
+    uint32_t *row = hist + (size_t)blockIdx.x * nblocks;
+    uint32_t carry = 0;
+    for (uint32_t i0 = 0; i0 < nblocks; i0 += RS_THREADS) {
+        const uint32_t i = i0 + threadIdx.x;
+        const uint32_t c = i < nblocks ? row[i] : 0u;
+        uint32_t sum;
+        const uint32_t ex = block_excl_scan<RS_WARPS>(c, sm, &sum);
+        if (i < nblocks) row[i] = carry + ex;
+        carry += sum;
+    }
+    if (threadIdx.x == 0) tot[blockIdx.x] = carry;
 }
 
 template <class KeyT>
 __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const KeyT *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                                                            uint32_t n, int shift, uint32_t nblocks, const uint32_t *__restrict__ gbase,
+                                                           const uint32_t *__restrict__ tot,
                                                            KeyT *__restrict__ keys_out, uint32_t *__restrict__ vals_out)
 {
     __shared__ uint32_t hw[RS_WARPS][256];                  // per-warp digit counts, then per-warp running output positions
+    __shared__ uint32_t sm[RS_WARPS + 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&hw[0][0])[i] = 0;
     __syncthreads();
@@ -97,7 +118,9 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const KeyT *__restric
     // (2) output position of every (warp, digit): the CTA's global base for the digit, then the warps in order
     {
         const uint32_t d = threadIdx.x;                       // RS_THREADS == 256 digits
-        uint32_t run = gbase[(size_t)d * nblocks + blockIdx.x];
+        uint32_t all;
+        const uint32_t dbase = block_excl_scan<RS_WARPS>(tot[d], sm, &all);            // keys with a smaller digit, over the whole input
+        uint32_t run = dbase + gbase[(size_t)d * nblocks + blockIdx.x];
 #pragma unroll
         for (int w = 0; w < RS_WARPS; ++w) { const uint32_t c = hw[w][d]; hw[w][d] = run; run += c; }
     }
@@ -120,12 +143,104 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const KeyT *__restric
         __syncwarp();
     }
 }
+
+// Small inputs (the planner's 4x10^4 query keys): ALL passes in one launch.  One cluster of 8 CTAs, each owning 8192
+// consecutive keys (a warp: 512); per pass the CTAs publish their digit totals in shared memory, read each other's over
+// DSMEM between two cluster barriers, and scatter through global memory (L2: loads bypass L1, the barrier's
+// release/acquire orders the stores).  Same order rule as the three-launch pass, so equally stable.
+constexpr int RC_THREADS = 512;
+constexpr int RC_WARPS = RC_THREADS / 32;
+constexpr int RC_ROUNDS = 16;
+constexpr int RC_CTAS = 8;
+constexpr uint32_t RC_TILE = RC_THREADS * RC_ROUNDS;
+constexpr uint32_t RC_MAX = RC_TILE * RC_CTAS;             // 65536 keys
+
+template <class KeyT>
+__global__ void __cluster_dims__(RC_CTAS, 1, 1) __launch_bounds__(RC_THREADS)
+k_rs_cluster(KeyT *ka, uint32_t *va, KeyT *kb, uint32_t *vb, uint32_t n, int passes)
+{
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ uint32_t hw[RC_WARPS][256];
+    __shared__ uint32_t ctot[256];                           // this CTA's digit totals, read by the whole cluster
+    __shared__ uint32_t sm[RC_WARPS + 1];
+    const uint32_t me = cluster.block_rank();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t wbase = me * RC_TILE + warp * (32 * RC_ROUNDS);
+    for (int p = 0; p < passes; ++p) {
+        const KeyT *ki = (p & 1) ? kb : ka;
+        const uint32_t *vi = (p & 1) ? vb : va;
+        KeyT *ko = (p & 1) ? ka : kb;
+        uint32_t *vo = (p & 1) ? va : vb;
+        const int shift = 8 * p;
+        for (int i = tid; i < RC_WARPS * 256; i += RC_THREADS) (&hw[0][0])[i] = 0;
+        __syncthreads();
+        KeyT k[RC_ROUNDS];
+        uint32_t v[RC_ROUNDS];
+#pragma unroll
+        for (int r = 0; r < RC_ROUNDS; ++r) {
+            const uint32_t i = wbase + r * 32 + lane;
+            k[r] = i < n ? __ldcg(ki + i) : (KeyT)0;
+            v[r] = i < n ? __ldcg(vi + i) : 0u;
+        }
+#pragma unroll
+        for (int r = 0; r < RC_ROUNDS; ++r) {
+            const bool valid = wbase + r * 32 + lane < n;
+            const uint32_t d = valid ? ((uint32_t)(k[r] >> shift) & 0xffu) : 256u + (uint32_t)lane;
+            const uint32_t mask = __match_any_sync(0xffffffffu, d);
+            if (valid && lane == __ffs((int)mask) - 1) hw[warp][d] += __popc(mask);
+            __syncwarp();
+        }
+        __syncthreads();
+        if (tid < 256) {
+            uint32_t c = 0;
+#pragma unroll
+            for (int w = 0; w < RC_WARPS; ++w) c += hw[w][tid];
+            ctot[tid] = c;
+        }
+        cluster.sync();
+        uint32_t before = 0, total = 0;
+        if (tid < 256) {
+#pragma unroll
+            for (uint32_t r = 0; r < (uint32_t)RC_CTAS; ++r) {
+                const uint32_t x = cluster.map_shared_rank(ctot, r)[tid];
+                total += x;
+                if (r < me) before += x;
+            }
+        }
+        uint32_t all;
+        const uint32_t dbase = block_excl_scan<RC_WARPS>(total, sm, &all);
+        if (tid < 256) {
+            uint32_t run = dbase + before;
+#pragma unroll
+            for (int w = 0; w < RC_WARPS; ++w) { const uint32_t c = hw[w][tid]; hw[w][tid] = run; run += c; }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < RC_ROUNDS; ++r) {
+            const bool valid = wbase + r * 32 + lane < n;
+            const uint32_t d = valid ? ((uint32_t)(k[r] >> shift) & 0xffu) : 256u + (uint32_t)lane;
+            const uint32_t mask = __match_any_sync(0xffffffffu, d);
+            const int leader = __ffs((int)mask) - 1;
+            uint32_t base = 0;
+            if (valid && lane == leader) { base = hw[warp][d]; hw[warp][d] = base + __popc(mask); }
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (valid) {
+                const uint32_t pos = base + __popc(mask & ((1u << lane) - 1u));
+                ko[pos] = k[r];
+                vo[pos] = v[r];
+            }
+            __syncwarp();
+        }
+        cluster.sync();                                       // every CTA has read ctot; this pass's stores are visible to the next
+    }
+}
 }  // namespace
 
 size_t radix_sort_temp_bytes(uint32_t n)
 {
     const uint32_t nblocks = (n + RS_TILE - 1) / RS_TILE;
-    return (size_t)256 * (nblocks ? nblocks : 1) * 4;
+    return (size_t)256 * (nblocks ? nblocks : 1) * 4 + 256 * 4;
 }
 
 // Sorts n (key, value) pairs by bits [0, end_bit) of the key.  (k0, v0) holds the input and is used as scratch; the result
@@ -138,6 +253,7 @@ cudaError_t radix_sort_pairs(KeyT *k0, uint32_t *v0, KeyT *k1, uint32_t *v1, uin
     int passes = (end_bit + 7) / 8;
     if (passes < 1) passes = 1;
     uint32_t *hist = reinterpret_cast<uint32_t *>(tmp);
+    uint32_t *tot = hist + (size_t)256 * nblocks;
     KeyT *ki = k0, *ko = k1;
     uint32_t *vi = v0, *vo = v1;
     if ((passes & 1) == 0) {                                  // an even number of passes ends where it began: start from the other side
@@ -146,11 +262,16 @@ cudaError_t radix_sort_pairs(KeyT *k0, uint32_t *v0, KeyT *k1, uint32_t *v1, uin
         if (c != cudaSuccess) return c;
         ki = k1; ko = k0; vi = v1; vo = v0;
     }
+    static const bool one_launch = [] { const char *e = std::getenv("HVS_SORT_CLUSTER"); return !(e && e[0] == '0'); }();
+    if (one_launch && n <= RC_MAX) {
+        k_rs_cluster<KeyT><<<RC_CTAS, RC_THREADS, 0, st>>>(ki, vi, ko, vo, n, passes);
+        return cudaGetLastError();
+    }
     for (int p = 0; p < passes; ++p) {
         const int shift = 8 * p;
         k_rs_hist<KeyT><<<nblocks, RS_THREADS, 0, st>>>(ki, n, shift, nblocks, hist);
-        k_rs_scan<<<1, RS_SCAN_T, 0, st>>>(hist, 256u * nblocks);
-        k_rs_scatter<KeyT><<<nblocks, RS_THREADS, 0, st>>>(ki, vi, n, shift, nblocks, hist, ko, vo);
+        k_rs_scan<<<256, RS_THREADS, 0, st>>>(hist, nblocks, tot);
+        k_rs_scatter<KeyT><<<nblocks, RS_THREADS, 0, st>>>(ki, vi, n, shift, nblocks, hist, tot, ko, vo);
         KeyT *tk = ki; ki = ko; ko = tk;
         uint32_t *tv = vi; vi = vo; vo = tv;
     }
