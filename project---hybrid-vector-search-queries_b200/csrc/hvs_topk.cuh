@@ -15,21 +15,28 @@ namespace hvs {
 
 constexpr uint64_t KEY_INF = 0xffffffffffffffffull;
 
-// In-place ascending bitonic sort of a[0..n) in shared memory, n a power of two, all `nthreads`
+// In-place ascending bitonic sort of a[0..n) in shared memory, n a power of two, all `nthreads` (a multiple of 32)
 // threads of the block participate.  Ends with a __syncthreads().
+// Every thread takes PAIRS (t -> elements i and i|j), so all lanes work and the exchange is branch-free; 32 consecutive
+// pairs with j <= 32 are one aligned run of 64 elements, the same run for every such j, so a step is separated from the
+// next by a warp barrier only -- a block barrier is needed just around the steps with j > 32 (512 keys: 9 instead of 45).
 __device__ __forceinline__ void block_bitonic_sort(uint64_t *a, int n, int tid, int nthreads)
 {
+    const int half = n >> 1;
     for (int k = 2; k <= n; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < n; i += nthreads) {
-                int ixj = i ^ j;
-                if (ixj > i) {
-                    uint64_t x = a[i], y = a[ixj];
-                    bool up = (i & k) == 0;
-                    if ((x > y) == up) { a[i] = y; a[ixj] = x; }
-                }
+            for (int t = tid; t < half; t += nthreads) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int ixj = i | j;
+                const uint64_t x = a[i], y = a[ixj];
+                const bool up = (i & k) == 0;
+                const uint64_t lo = x < y ? x : y, hi = x < y ? y : x;
+                a[i] = up ? lo : hi;
+                a[ixj] = up ? hi : lo;
             }
-            __syncthreads();
+            const int next_j = j > 1 ? (j >> 1) : (k < n ? k : 64);    // the step after this one (64: the end, block barrier)
+            if (j > 32 || next_j > 32) __syncthreads();
+            else __syncwarp();
         }
     }
 }
