@@ -169,10 +169,24 @@ struct PlanParams {
     bool approx_ok = true;                // false: the index allows no approximate sweep (Index::approx_ok)
 };
 
-constexpr uint64_t SHARD_QUERY_COST = 6000000;  // shard_assign: fixed cost of a query in (query,row) pairs -- threshold warm-up, finalize; measured on 2 GPUs:
-                                                // per-rank solve times 16.9|19.5 ms at 4e5, 17.2|18.7 at 2e6, 18.0|18.4 at 6e6.  HVS_SHARD_QCOST overrides
+// shard_assign's cost of a query, in (query,row) pairs: its rows plus a fixed part -- threshold warm-up, list merges,
+// finalize -- that grows with the slice (SHARD_ROW_COST per row) up to SHARD_QUERY_COST: a long slice is swept in many
+// chunks at once and warms a threshold up in each of them, a category's few chunks do it once.  Measured (every rank's
+// share of the headline batch, tools/shard_all_ranks.py): K3 time per rank = 1.4-2.0 ms per 10^10 pairs + 2.3 us per
+// T-range query (13-16 x 10^6 pairs' worth) + 0.18 us per category query (10^5 / 3x10^4 rows: ~10^6); a flat 6x10^6 per
+// query left the ranks at 5.30-6.05 ms.  HVS_SHARD_QCOST / HVS_SHARD_ROWCOST override (ROWCOST 0: flat).
+constexpr uint64_t SHARD_QUERY_COST = 14000000;
+constexpr uint64_t SHARD_ROW_COST = 14;
 uint64_t shard_query_cost();
-constexpr uint32_t SHARD_STRIPES = 16;          // shard_assign: segments per rank
+uint64_t shard_row_cost();
+__host__ __device__ inline unsigned long long shard_cost_of(uint32_t len, unsigned long long qcost, unsigned long long rowcost)
+{
+    const unsigned long long rows = len > (uint32_t)K ? len : (uint32_t)K;
+    const unsigned long long grow = rows * rowcost;
+    return rows + ((rowcost && grow < qcost) ? grow : qcost);
+}
+constexpr uint32_t SHARD_STRIPES = 16;          // shard_assign: segments per rank (T arena)
+constexpr uint32_t SHARD_STRIPES_CT = 2;        // ... in the (C,T) arena: a category's queries share its rows and fill items together -- few cuts
 void shard_assign(const QSlice *slices, uint32_t m, uint32_t world, uint32_t *order, uint32_t *counts);
 void plan_build(const QSlice *slices, uint32_t m, const PlanParams &pp, Plan &out);     // begin + every group + finish
 

@@ -484,6 +484,12 @@ uint64_t shard_query_cost()
     return v;
 }
 
+uint64_t shard_row_cost()
+{
+    static const uint64_t v = [] { const char *s = getenv("HVS_SHARD_ROWCOST"); long long k = s ? atoll(s) : -1; return k >= 0 ? (uint64_t)k : SHARD_ROW_COST; }();
+    return v;
+}
+
 uint32_t shard_stripes(uint32_t m, uint32_t world)
 {
     static const uint32_t env = [] { const char *s = getenv("HVS_SHARD_STRIPES"); int k = s ? atoi(s) : 0; return (uint32_t)(k > 0 ? k : 0); }();
@@ -502,23 +508,27 @@ void shard_assign(const QSlice *sl, uint32_t m, uint32_t world, uint32_t *order,
     for (uint32_t i = 0; i < m; ++i) keys[sl[i].arena & 1u].push_back({((uint64_t)sl[i].begin << 32) | sl[i].end, i});
     radix_sort_keys(keys[0]);
     radix_sort_keys(keys[1]);
-    const uint64_t qcost = shard_query_cost();
-    auto cost_of = [&](uint32_t i) { return (uint64_t)std::max(sl[i].end - sl[i].begin, (uint32_t)K) + qcost; };
-    uint64_t total = 0;
-    for (uint32_t i = 0; i < m; ++i) total += cost_of(i);
-    const uint64_t nseg = (uint64_t)world * shard_stripes(m, world);
-    const bool fits64 = (unsigned __int128)total * nseg < ((unsigned __int128)1 << 63);   // then plain 64-bit arithmetic (what the device kernel uses)
+    const uint64_t qcost = shard_query_cost(), rowcost = shard_row_cost();
+    auto cost_of = [&](uint32_t i) { return (uint64_t)shard_cost_of(sl[i].end - sl[i].begin, qcost, rowcost); };
+    // each arena's cost is cut into segments of its own: every rank gets its share of BOTH (a category query costs a
+    // tenth of a range query; one cut over the whole order would hand all of them to a few ranks)
+    const uint32_t stripes = shard_stripes(m, world);
     std::vector<uint8_t> owner(m);
-    uint64_t cum = 0;
-    for (int a = 0; a < 2; ++a)
+    for (int a = 0; a < 2; ++a) {
+        const uint64_t nseg = (uint64_t)world * (a ? std::min(stripes, SHARD_STRIPES_CT) : stripes);
+        uint64_t total = 0;
+        for (const auto &kv : keys[a]) total += cost_of(kv.second);
+        const bool fits64 = (unsigned __int128)total * nseg < ((unsigned __int128)1 << 63);   // then plain 64-bit arithmetic (what the device kernel uses)
+        uint64_t cum = 0;
         for (const auto &kv : keys[a]) {
             const uint64_t c = cost_of(kv.second);
             // the segment that holds the midpoint of this query's cost interval
             uint64_t seg = fits64 ? (cum + c / 2) * nseg / total : (uint64_t)((unsigned __int128)(cum + c / 2) * nseg / total);
             if (seg >= nseg) seg = nseg - 1;
-            owner[kv.second] = (uint8_t)(seg % world);
+            owner[kv.second] = (uint8_t)((seg + (a ? world / 2 : 0u)) % world);
             cum += c;
         }
+    }
     for (uint32_t i = 0; i < m; ++i) ++counts[owner[i]];
     std::vector<uint32_t> off(world + 1, 0);
     for (uint32_t r = 0; r < world; ++r) off[r + 1] = off[r] + counts[r];

@@ -369,7 +369,7 @@ __global__ void k_sa_keys(const QSlice *__restrict__ sl, uint32_t m, uint32_t nb
 
 // One CTA: cumulative cost along the (arena, begin, end) order -> segment -> owner rank; queries per rank.
 __global__ void __launch_bounds__(SCAN_T) k_sa_assign(const QSlice *__restrict__ sl, const uint32_t *__restrict__ vals, uint32_t m,
-                                                      uint32_t world, uint32_t stripes, unsigned long long query_cost,
+                                                      uint32_t world, uint32_t stripes, unsigned long long query_cost, unsigned long long row_cost,
                                                       uint32_t *__restrict__ owner /* [m], by sorted position */,
                                                       uint32_t *__restrict__ counts /* [world] */)
 {
@@ -378,21 +378,31 @@ __global__ void __launch_bounds__(SCAN_T) k_sa_assign(const QSlice *__restrict__
     if (threadIdx.x < 256) scnt[threadIdx.x] = 0;
     const uint32_t per = (m + SCAN_T - 1) / SCAN_T;
     const uint32_t t0 = min(m, threadIdx.x * per), t1 = min(m, t0 + per);
-    auto cost_of = [&](uint32_t t) {
+    auto cost_of = [&](uint32_t t, uint32_t *arena) {
         const QSlice s = sl[vals[t]];
-        const uint32_t len = s.end - s.begin;
-        return (unsigned long long)(len > (uint32_t)K ? len : (uint32_t)K) + query_cost;
+        *arena = s.arena & 1u;
+        return shard_cost_of(s.end - s.begin, query_cost, row_cost);
     };
-    unsigned long long mine = 0;
-    for (uint32_t t = t0; t < t1; ++t) mine += cost_of(t);
-    unsigned long long total;
-    unsigned long long cum = block_excl_scan<unsigned long long>(mine, &total, sm64);      // has the barriers scnt needs
-    const unsigned long long nseg = (unsigned long long)world * stripes;
+    // the sorted order holds the T arena's queries, then the (C,T) arena's: each arena's cost is cut into segments of
+    // its own, so every rank gets its share of BOTH (a category query costs a tenth of a range query)
+    unsigned long long mine = 0, mine0 = 0;
     for (uint32_t t = t0; t < t1; ++t) {
-        const unsigned long long c = cost_of(t);
-        unsigned long long seg = (cum + c / 2) * nseg / total;       // the segment that holds the midpoint of this query's cost interval
+        uint32_t a;
+        const unsigned long long c = cost_of(t, &a);
+        mine += c;
+        if (a == 0) mine0 += c;
+    }
+    unsigned long long total, total0;
+    unsigned long long cum = block_excl_scan<unsigned long long>(mine, &total, sm64);      // has the barriers scnt needs
+    block_excl_scan<unsigned long long>(mine0, &total0, sm64);
+    for (uint32_t t = t0; t < t1; ++t) {
+        uint32_t a;
+        const unsigned long long c = cost_of(t, &a);
+        const unsigned long long nseg = (unsigned long long)world * (a ? min(stripes, SHARD_STRIPES_CT) : stripes);
+        const unsigned long long cum_a = a ? cum - total0 : cum, total_a = a ? total - total0 : total0;
+        unsigned long long seg = (cum_a + c / 2) * nseg / total_a;     // the segment that holds the midpoint of this query's cost interval
         if (seg >= nseg) seg = nseg - 1;
-        const uint32_t o = (uint32_t)(seg % world);
+        const uint32_t o = (uint32_t)((seg + (a ? world / 2 : 0u)) % world);
         owner[t] = o;
         atomicAdd(&scnt[o], 1u);
         cum += c;
@@ -449,7 +459,7 @@ cudaError_t shard_assign_dev(hvs_engine *e, const QSlice *d_sl, uint32_t m, uint
     PDCK(P.sort_tmp.ensure(radix_sort_temp_bytes(m)));
     PDCK(radix_sort_pairs<uint64_t>(P.keys_in.as<uint64_t>(), P.vals_in.as<uint32_t>(), P.keys.as<uint64_t>(), P.vals.as<uint32_t>(), m, end_bit,
                                     P.sort_tmp.p, s));
-    k_sa_assign<<<1, SCAN_T, 0, s>>>(d_sl, P.vals.as<uint32_t>(), m, world, stripes, shard_query_cost(), P.sa_owner_in.as<uint32_t>(),
+    k_sa_assign<<<1, SCAN_T, 0, s>>>(d_sl, P.vals.as<uint32_t>(), m, world, stripes, shard_query_cost(), shard_row_cost(), P.sa_owner_in.as<uint32_t>(),
                                      P.sa_counts.as<uint32_t>());
     // stable sort by owner (one 8-bit pass): rank-major, each rank's queries keep the (arena, begin, end) order
     PDCK(radix_sort_pairs<uint32_t>(P.sa_owner_in.as<uint32_t>(), P.vals.as<uint32_t>(), P.sa_owner.as<uint32_t>(), P.sa_order.as<uint32_t>(), m, 8,

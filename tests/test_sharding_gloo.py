@@ -144,7 +144,8 @@ def _headline_like_slices(m, n, ncat, seed):
 def test_shard_assign_balance_locality_determinism(hvs):
     n, m, ncat = 10_000_000, 40_000, 100
     t, arena, begin, end, cat = _headline_like_slices(m, n, ncat, 7)
-    cost = np.maximum(end - begin, 100).astype(np.int64) + 6_000_000
+    rows = np.maximum(end - begin, 100).astype(np.int64)
+    cost = rows + np.minimum(14 * rows, 14_000_000)       # hvs_engine.h shard_cost_of: rows + a fixed part that grows with the slice
     for world in (1, 2, 4, 8):
         order, counts = hvs.shard_assign(arena, begin, end, world)
         order2, counts2 = hvs.shard_assign(arena, begin, end, world)
