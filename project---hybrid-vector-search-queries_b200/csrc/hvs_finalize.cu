@@ -15,6 +15,16 @@
 
 namespace hvs {
 
+#ifndef HVS_K5_BATCH
+#define HVS_K5_BATCH 0         // 1: phase 2 loads a whole row before summing it (128 registers instead of 80: 4 CTAs per SM
+                               // instead of 6 -- measured 1.95 ms against 1.45 on the headline, so off)
+#endif
+
+#ifndef HVS_K5_MINBLOCKS
+#define HVS_K5_MINBLOCKS 7     // CTAs per SM the register allocation aims at: 72 registers; measured K5 1.33-1.36 ms against 1.39-1.43 at 6 (80
+                               // registers) and 1.70-1.73 at 8 (64 registers, spills)
+#endif
+
 namespace {
 constexpr int FT = 128;        // threads
 constexpr int P1CAP = 2048;    // approximate-score selection buffer (>= P1KEEP + 4 lists of KOUT)
@@ -26,7 +36,7 @@ struct FinSmem {
 };
 }  // namespace
 
-__global__ void __launch_bounds__(FT)
+__global__ void __launch_bounds__(FT, HVS_K5_MINBLOCKS)
 k_finalize(const float *__restrict__ queries, const QSlice *__restrict__ slices, const uint32_t *__restrict__ tile_q,
            const uint32_t *__restrict__ qoff, const uint32_t *__restrict__ qlists, const uint64_t *__restrict__ cand,
            const uint32_t *__restrict__ cand_cnt, uint32_t *__restrict__ flags, Arena a0, Arena a1,
@@ -99,10 +109,34 @@ k_finalize(const float *__restrict__ queries, const QSlice *__restrict__ slices,
     // a K3 pool can pick them up while a query has no threshold yet -- because the pass below scores ALL of them.
     const int c1 = (int)S.p1.cnt;
     const float INF = __int_as_float(0x7f800000);
-    for (int i = tid; i < c1; i += FT) {
-        const uint32_t row = (uint32_t)S.p1.cand[i];
+    for (int i0 = 0; i0 < c1; i0 += FT) {                         // block-uniform trip count
+        const int i = i0 + tid;
+        const bool valid = i < c1;
+        const uint32_t row = (uint32_t)S.p1.cand[valid ? i : 0];  // lanes past the end re-read entry 0 (no divergence before the barrier)
+#if HVS_K5_BATCH
+        // The whole row first -- 25 independent 16-byte loads in flight, ONE round trip to HBM instead of five (the rows
+        // are scattered: this phase is latency-bound) -- then the reference's sequential sum; the warp barrier keeps
+        // the compiler from sinking the loads into the dependent add chain (k_small does the same).
+        float d;
+        {
+            const float4 *x4 = reinterpret_cast<const float4 *>(A.x + (size_t)row * DIM);
+            const float4 *q4 = reinterpret_cast<const float4 *>(S.q);
+            float4 xr[DIM / 4];
+#pragma unroll
+            for (int j = 0; j < DIM / 4; ++j) xr[j] = __ldg(x4 + j);
+            __syncwarp();
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < DIM / 4; ++j) acc = ref_accum4(acc, xr[j], q4[j]);
+            d = acc;
+        }
+        if (!valid) continue;
+        if (A.n_outl && !(A.xnorm[row] < INF)) continue;
+#else
+        if (!valid) continue;
         if (A.n_outl && !(A.xnorm[row] < INF)) continue;
         const float d = ref_dist_row(A.x + (size_t)row * DIM, S.q);
+#endif
         S.p2.push(d, row);                                        // <= P1KEEP entries
         if (audit) {
             // HVS_FLAG_MARGIN_AUDIT: the bound the margins rest on, measured.  s~ is in units of sx^2 d for K3 lists; the
