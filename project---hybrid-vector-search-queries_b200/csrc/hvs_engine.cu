@@ -308,7 +308,7 @@ static int solve_core_dev(hvs_engine *e, const float *q_dev, uint32_t m, const Q
     }
     PlanHeader h{};
     ECUDA(plan_dev_begin(e, d_sl, m, cfg, &h));                  // the one host round trip of the plan: a 112-byte header
-    st.launches += 9;
+    st.launches += e->pdev.launches;
     st.pairs = h.pairs;
     st.pairs_tile = h.pairs_tile;
     st.pairs_direct = h.pairs - h.pairs_tile;
@@ -635,9 +635,11 @@ extern "C" int hvs_solve_shard_device(hvs_engine *e, const float *queries_dev, u
     const bool on_device = use_device_planner(e) && (double)m * ((double)e->index.n + (double)shard_query_cost()) * world * stripes < 9.0e18;
     const uint32_t *own_dev = nullptr;
     uint32_t off = 0, m_own = 0;
+    uint32_t sa_launches = 0;
     if (on_device) {
         uint32_t *order_dev = nullptr, *counts_dev = nullptr;
         ECUDA(shard_assign_dev(e, d_sl_all, m, world, stripes, &order_dev, &counts_dev));
+        sa_launches = e->pdev.launches;
         ECUDA(e->h_stage_own.ensure((size_t)m * 4 + 256 * 4));
         uint32_t *h_order = e->h_stage_own.as<uint32_t>(), *h_counts = h_order + m;
         if (out_order_host) ECUDA(cudaMemcpyAsync(h_order, order_dev, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
@@ -671,7 +673,7 @@ extern "C" int hvs_solve_shard_device(hvs_engine *e, const float *queries_dev, u
     e->shard_m = m;
     e->shard_world = world;
     reset_solve_stats(e, m_own);
-    e->stats.launches = on_device ? 6 : 1;
+    e->stats.launches = 1u + sa_launches;                   // the slice search over all m, the assignment's kernels
     if (m_own) {
         ECUDA(e->d_shard_q.ensure((size_t)m_own * QROW * 4));
         ECUDA(e->d_shard_sl.ensure((size_t)m_own * sizeof(QSlice)));

@@ -224,6 +224,7 @@ struct PlanDev {
     DevBuf header, diff, pref, cls, keys_in, keys, vals_in, vals, nch, qoff, cdiff, cbeg, cstart, ibase, ibase_rest, nrest, sort_tmp;
     DevBuf sa_owner_in, sa_owner, sa_order, sa_counts;     // query sharding
     uint32_t nb = 0;
+    uint32_t launches = 0;                                  // kernels launched by the last plan_dev_begin / shard_assign_dev
 };
 void plan_begin(const QSlice *slices, uint32_t m, const PlanParams &pp, Plan &out);     // classify, order, cut into groups
 void plan_group(const QSlice *slices, Plan &out, size_t g, uint32_t &item_begin, uint32_t &item_end);   // items of one group
@@ -301,6 +302,7 @@ cudaError_t measure_ffma_peak(hvs_engine *e, uint32_t iters, float *tflops, floa
 // hvs_sort.cu: stable LSD radix sort of (key, u32 value) pairs by key bits [0, end_bit); (k0, v0) = input AND scratch, the
 // result lands in (k1, v1); tmp = radix_sort_temp_bytes(n) bytes
 size_t radix_sort_temp_bytes(uint32_t n);
+uint32_t radix_sort_launches(uint32_t n, int end_bit);
 template <class KeyT>
 cudaError_t radix_sort_pairs(KeyT *k0, uint32_t *v0, KeyT *k1, uint32_t *v1, uint32_t n, int end_bit, void *tmp, cudaStream_t st);
 // device planner: everything up to the header read-back (one stream sync); then the chunk lists, items and K5's list index

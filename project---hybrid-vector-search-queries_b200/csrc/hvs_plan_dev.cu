@@ -462,6 +462,7 @@ cudaError_t shard_assign_dev(hvs_engine *e, const QSlice *d_sl, uint32_t m, uint
     k_sa_assign<<<1, SCAN_T, 0, s>>>(d_sl, P.vals.as<uint32_t>(), m, world, stripes, shard_query_cost(), shard_row_cost(), P.sa_owner_in.as<uint32_t>(),
                                      P.sa_counts.as<uint32_t>());
     // stable sort by owner (one 8-bit pass): rank-major, each rank's queries keep the (arena, begin, end) order
+    P.launches = 2u + radix_sort_launches(m, end_bit) + radix_sort_launches(m, 8);
     PDCK(radix_sort_pairs<uint32_t>(P.sa_owner_in.as<uint32_t>(), P.vals.as<uint32_t>(), P.sa_owner.as<uint32_t>(), P.sa_order.as<uint32_t>(), m, 8,
                                     P.sort_tmp.p, s));
     PDCK(cudaGetLastError());
@@ -516,6 +517,7 @@ cudaError_t plan_dev_begin(hvs_engine *e, const QSlice *d_sl, uint32_t m, const 
     PDCK(P.sort_tmp.ensure(radix_sort_temp_bytes(m)));
     PDCK(radix_sort_pairs<uint64_t>(P.keys_in.as<uint64_t>(), P.vals_in.as<uint32_t>(), P.keys.as<uint64_t>(), P.vals.as<uint32_t>(), m, end_bit,
                                     P.sort_tmp.p, s));
+    P.launches = (cfg.tile_allowed ? 7u : 5u) + radix_sort_launches(m, end_bit);    // depth, cells, classify, params, keys, the sort, chunks, scan
     k_pd_chunks<<<gb, 256, 0, s>>>(P.keys.as<uint64_t>(), P.vals.as<uint32_t>(), m, nb, d_sl, H, P.cdiff.as<int>(), P.cbeg.as<uint32_t>(),
                                    P.nch.as<uint32_t>());
     k_pd_scan<<<1, SCAN_T, 0, s>>>(H, P.cdiff.as<int>(), cfg.bq, P.cbeg.as<uint32_t>(), cfg.seed_phase, P.cstart.as<uint32_t>(), P.ibase.as<uint32_t>(),

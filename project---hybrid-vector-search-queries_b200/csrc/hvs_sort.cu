@@ -237,6 +237,15 @@ k_rs_cluster(KeyT *ka, uint32_t *va, KeyT *kb, uint32_t *vb, uint32_t n, int pas
 }
 }  // namespace
 
+// kernel launches radix_sort_pairs makes for n keys of end_bit bits (the engine's launch count is a claim the bench reports)
+uint32_t radix_sort_launches(uint32_t n, int end_bit)
+{
+    if (!n) return 0;
+    const int passes = end_bit > 8 ? (end_bit + 7) / 8 : 1;
+    static const bool one_launch = [] { const char *e = std::getenv("HVS_SORT_CLUSTER"); return !(e && e[0] == '0'); }();
+    return (one_launch && n <= RC_MAX) ? 1u : 3u * (uint32_t)passes;
+}
+
 size_t radix_sort_temp_bytes(uint32_t n)
 {
     const uint32_t nblocks = (n + RS_TILE - 1) / RS_TILE;
