@@ -98,7 +98,7 @@ typedef struct hvs_stats {
     uint32_t launches;          /* kernels launched by the last solve */
     float ms_index_build;       /* last hvs_index_build*, device time */
     float ms_h2d;               /* query upload (host entry points only) */
-    float ms_plan;              /* slice search kernel + host planner + work-list upload */
+    float ms_plan;              /* slice search kernel + planner (device kernels and their sort; one 112-byte read-back) */
     float ms_direct;            /* K4 */
     float ms_tile;              /* K2 + K3 */
     float ms_tile_ffma;         /* K2 alone (sum of its launches) */
